@@ -1,0 +1,184 @@
+/*
+ * sdaopt_b200.h -- C ABI of the B200-native dual-annealing hot path (libsdaopt_b200.so).
+ *
+ * Drop-in boundary for sgubianpm/sdaopt's `sda()` / `SDARunner.search()` path.  The reference is
+ * pure Python, so the "FFI" a maintainer binds is ctypes; every entry point
+ * below names the reference interface it replaces (file:line under the reference checkout).
+ *
+ * Conventions
+ *  - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *  - "_host" entry points take HOST pointers and perform allocation, H2D, launch, D2H and a stream
+ *    synchronize internally; the others take DEVICE pointers, never allocate and never synchronize
+ *  - every function returns SDA_OK (0) or a negative SDA_E_* code; sda_error_string() decodes it;
+ *    there is no CPU fallback: without a usable CUDA device the calls fail with SDA_E_CUDA
+ *  - all arithmetic is IEEE double; chains are independent; one launch = one problem
+ *
+ * RNG protocol (production mode, SDA_RNG_PHILOX): every uniform is a pure function of
+ *     Philox4x32-10( ctr = { k, attempt, (purpose << 24) | j, iter }, key = seed[chain] )
+ * with  k       coordinate index (0 where not applicable)
+ *       attempt polar-rejection retry / re-initialisation counter
+ *       purpose 0 polar pair, 1 tail-clip uniforms, 2 acceptance uniform, 3 (re)initial location
+ *       j       Markov-chain index inside the temperature step (0xFFFFFF outside a step)
+ *       iter    SDARunner._iter (_sda.py:403), 0 before the first step
+ * One block yields two 53-bit uniforms ((w0>>5)*2^26 + (w1>>6))/2^53, ((w2>>5)*2^26 + (w3>>6))/2^53
+ * -- the construction of numpy's RandomState.random_sample().  In SDA_RNG_TAPE mode the uniforms
+ * are consumed sequentially from a caller-supplied tape in exactly the reference's draw order
+ * (SURVEY.md App. A.1), which reproduces a reference trajectory.
+ */
+#ifndef SDAOPT_B200_H
+#define SDAOPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDA_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define SDA_OK 0
+#define SDA_E_INVALID (-1)    /* bad argument */
+#define SDA_E_BOUNDS (-2)     /* not all(lower < upper): ValueError of _sda.py:366-367 */
+#define SDA_E_CUDA (-3)       /* CUDA runtime error / no device (see sda_last_cuda_error) */
+#define SDA_E_WORKSPACE (-4)  /* workspace too small */
+#define SDA_E_UNSUPPORTED (-5)
+
+/* ---- registered device objectives (replace the Python callable `func`, _sda.py:440-444) ----- */
+enum {
+    SDA_FN_RASTRIGIN = 0,         /* go_benchmark_functions/go_funcs_R.py:88-91 */
+    SDA_FN_SHIFTED_RASTRIGIN = 1, /* README.md:61-71; params[0] = shift */
+    SDA_FN_ROSENBROCK = 2,        /* go_funcs_R.py:288-291 */
+    SDA_FN_ACKLEY01 = 3,          /* go_funcs_A.py:43-48 */
+    SDA_FN_SCHWEFEL01 = 4,        /* go_funcs_S.py:332-336 */
+    SDA_FN_SCHWEFEL26 = 5,        /* go_funcs_S.py:613-616 */
+    SDA_FN_EXPONENTIAL = 6,       /* go_funcs_E.py:303-306 */
+    SDA_FN_SUTTON_CHEN = 7,       /* benchmark/suttonchen.py:23-40 */
+    SDA_FN_CONSTANT = 8,          /* tests/test_sda.py:34 `weirdfunc`; params[0] = value */
+    SDA_FN_SPHERE = 9,            /* go_funcs_S.py:1156-1159 */
+    SDA_FN_GRIEWANK = 10,         /* go_funcs_G.py:171-175 */
+    SDA_FN_COUNT
+};
+
+enum { SDA_RNG_PHILOX = 0, SDA_RNG_TAPE = 1 };
+
+/* decision codes of the optional per-evaluation trace */
+enum { SDA_DEC_IMPROVE = 1, SDA_DEC_NEW_BEST = 2, SDA_DEC_METRO_ACCEPT = 3, SDA_DEC_REJECT = 4 };
+
+/* per-chain status bits (SdaResult.status) */
+enum {
+    SDA_CHAIN_OK = 0,
+    SDA_CHAIN_REINIT_FAILED = 1, /* ValueError of _sda.py:149-156 (1000 re-inits) */
+    SDA_CHAIN_TAPE_EXHAUSTED = 2
+};
+
+/* The optimisation problem: replaces (func, bounds) of sda(), _sda.py:431-452. */
+typedef struct SdaProblem {
+    int32_t functor;      /* SDA_FN_* */
+    int32_t dim;          /* len(bounds) */
+    const double *lower;  /* [dim] */
+    const double *upper;  /* [dim] */
+    const double *params; /* functor parameters or NULL */
+    int32_t n_params;
+} SdaProblem;
+
+/* Replaces the keyword arguments of sda() (_sda.py:431-433) plus the constants the reference
+ * hard-codes (temperature_restart :385; L-BFGS-B option dict :300-311) and the suite's first-hit
+ * monitor (benchmark/bench.py:292-321). */
+typedef struct SdaConfig {
+    int64_t maxiter;            /* 1000 */
+    double initial_temp;        /* 5230. */
+    double visit;               /* qv 2.62 */
+    double accept;              /* qa -5.0 */
+    double maxfun;              /* 1e7 (soft limit with the reference's semantics) */
+    int32_t pure_sa;            /* no local search */
+    double temperature_restart; /* 0.1 */
+    int32_t rng_mode;           /* SDA_RNG_* */
+    int64_t max_calls;          /* suite budget MAX_FN_CALL (0 = monitor off) */
+    double fglob;               /* suite: known optimum */
+    double tol;                 /* suite: DEFAULT_TOL 1e-8 */
+    int64_t trace_len;          /* evaluations traced per chain (0 = off) */
+    /* K1 tables indexed by the step index i of _sda.py:398 (host pointers, always): T_i and
+     * sigmax(T_i) computed by the caller with the reference's own formulas.  NULL -> the library
+     * computes them with libm. */
+    const double *temp_table;
+    const double *sigmax_table;
+    int64_t table_len;
+} SdaConfig;
+
+/* Replaces SDARunner.result (_sda.py:420-428) for a batch of chains, plus the suite's per-run
+ * record (bench.py:184-188).  Any pointer except x/fun/nit/ncall/status may be NULL. */
+typedef struct SdaResult {
+    double *x;           /* [C*dim] res.x   */
+    double *fun;         /* [C]     res.fun */
+    int64_t *nit;        /* [C]     res.nit */
+    int64_t *ncall;      /* [C]     res.ncall */
+    int64_t *ncall_ls;   /* [C] evaluations spent inside local searches */
+    int64_t *n_ls;       /* [C] local searches started */
+    int32_t *status;     /* [C] SDA_CHAIN_* bits */
+    int32_t *hit;        /* [C] suite: success */
+    int64_t *ncall_hit;  /* [C] suite: call index of the first hit (max_calls on failure) */
+    double *f_hit;       /* [C] suite: value at the first hit (inf on failure) */
+    double *trace_e;     /* [C*trace_len] */
+    uint8_t *trace_d;    /* [C*trace_len] */
+    int64_t *tape_used;  /* [C] uniforms consumed (tape mode) */
+} SdaResult;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int sda_abi_version(void);
+const char *sda_error_string(int code);
+const char *sda_last_cuda_error(void);
+/* functor id for a registered name ("Rastrigin", ...), or SDA_E_INVALID */
+int sda_functor_id(const char *name);
+const char *sda_functor_name(int functor);
+/* number of CUDA devices visible, or SDA_E_CUDA */
+int sda_device_count(void);
+
+/* ---- the hot path: replaces sda(...) -> SDARunner.__init__ + search() + result
+ *      (_sda.py:585-589, :357-428) for n_chains independent runs ------------------------------- */
+/* bytes of device scratch sda_batch_run needs for this (problem, config, n_chains) */
+size_t sda_workspace_bytes(const SdaProblem *p, const SdaConfig *c, int64_t n_chains);
+
+/* DEVICE-pointer form.  p->lower/upper/params, x0, seeds, tape, out->* and workspace are device
+ * pointers (c->temp_table / sigmax_table stay host pointers).  Asynchronous on `stream`.
+ *   x0    [C*dim] or NULL -> uniform initial location, _sda.py:137-138
+ *   seeds [C]     Philox keys (NULL -> key = chain index); ignored in tape mode
+ *   tape  [C*tape_len] uniforms (tape mode) */
+int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_chains, const double *x0,
+                  const uint64_t *seeds, const double *tape, int64_t tape_len, const SdaResult *out,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* HOST-pointer form of the same call (what the ctypes binding of sda() uses): allocates, copies
+ * in, runs on `device`, copies out, synchronizes. */
+int sda_batch_run_host(const SdaProblem *p, const SdaConfig *c, int64_t n_chains, const double *x0,
+                       const uint64_t *seeds, const double *tape, int64_t tape_len,
+                       const SdaResult *out, int device);
+
+/* ---- objective evaluation: replaces Benchmark.fun(x) / sutton_chen(x)
+ *      (go_benchmark_functions/go_benchmark.py:15, suttonchen.py:23) for n points ----------------- */
+int sda_eval(const SdaProblem *p, const double *x, int64_t n, double *f, void *stream);
+int sda_eval_host(const SdaProblem *p, const double *x, int64_t n, double *f, int device);
+
+/* ---- unit-test surface mirroring sdaopt/__init__.py:9-13 (host pointers) ------------------------ */
+/* VisitingDistribution.visiting(x, step, temperature) (_sda.py:40-73) driven by a tape of
+ * uniforms; writes x_visit[dim] and the number of uniforms consumed */
+int sda_visiting_host(const SdaProblem *p, double qv, const double *x, int64_t step,
+                      double temperature, double sigmax, const double *tape, int64_t tape_len,
+                      double *x_visit, int64_t *tape_used, int device);
+/* n successive VisitingDistribution.visit_fn(temperature) values (_sda.py:75-91) */
+int sda_visit_fn_host(double qv, double sigmax, const double *tape, int64_t tape_len, double *out,
+                      int64_t n, int64_t *tape_used, int device);
+/* ObjectiveFunWrapper.local_search(x) (_sda.py:347-351) for n start points: batched projected
+ * L-BFGS-B with the reference's option dict (:300-311) and clipped central-difference gradient
+ * (:325-345).  success[i] mirrors mres.success; nfev[i] counts objective calls. */
+int sda_local_search_host(const SdaProblem *p, const double *x_in, int64_t n, double *x_out,
+                          double *f_out, int32_t *success, int64_t *nfev, int device);
+
+/* ---- measurement helper: sustained FP64 FMA rate of the device (roofline denominator) ----------- */
+int sda_fp64_peak(double *tflops, double *ms, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -7,6 +7,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -854,7 +855,11 @@ int orc_lbfgsb_minimize(int n, const double *l, const double *u, double *x, doub
                     if (gd >= 0.0) { info = -4; }
                 }
                 if (info == 0) {
+                    double stp_in = stp;
                     lstask = dcsrch(&ls, first, f, gd, &stp, 1e-3, 0.9, 0.1, 0.0, stpmx);
+                    if (getenv("ORC_TRACE_LNS"))
+                        fprintf(stderr, "lns iter=%d ifun=%d first=%d f=%.17g gd=%.6e stp_in=%.17g stp_out=%.17g task=%d stpmx=%.6e col=%d\n",
+                                iter, ifun, first, f, gd, stp_in, stp, lstask, stpmx, col);
                     first = 0;
                     if (lstask == LS_ERROR) lstask = LS_FG; /* treated like the reference: keeps going */
                     if (lstask == LS_FG) {

@@ -12,6 +12,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -256,6 +257,12 @@ typedef struct {
     double f_hit;
     /* scratch */
     double *x_visit, *visits, *gx1, *gx2;
+    /* scipy ScalarFunction cache (optimize/_differentiable_functions.py fun_and_grad): a request
+     * at an x bit-identical to the last evaluated one returns the stored f, g without calling
+     * the objective */
+    double *ls_x, *ls_g;
+    double ls_f;
+    int ls_cache_valid;
     /* gaussian_fn state _sda.py:36-38 */
     double x_gauss, s_gauss, root_gauss;
     /* trace */
@@ -470,7 +477,16 @@ static int fun_and_grad(void *ctx, const double *x, double *f, double *g)
     Chain *ch = (Chain *)ctx;
     const int n = ch->dim;
     const double reps = 1.e-6;  /* _sda.py:315 */
+    if (ch->ls_cache_valid && memcmp(ch->ls_x, x, sizeof(double) * n) == 0) {
+        *f = ch->ls_f;
+        memcpy(g, ch->ls_g, sizeof(double) * n);
+        return 0;
+    }
     *f = func_wrapper(ch, x);   /* ScalarFunction.fun_and_grad: f first, then jac(x) */
+    if (getenv("ORC_TRACE")) {  /* debugging aid: dump the fun_and_grad request points */
+        FILE *fp = fopen("/tmp/orc_trace.txt", ch->nb_fun_call == 1 ? "w" : "a");
+        if (fp) { for (int i = 0; i < n; ++i) fprintf(fp, "%.17g ", x[i]); fprintf(fp, "\n"); fclose(fp); }
+    }
     if (ch->stop) return 1;
     for (int i = 0; i < n; ++i) {
         memcpy(ch->gx1, x, sizeof(double) * n);
@@ -493,6 +509,10 @@ static int fun_and_grad(void *ctx, const double *x, double *f, double *g)
         g[i] = (f1 - f2) / (respl + respr);
         if (isnan(g[i]) || isinf(g[i])) g[i] = 101.0;
     }
+    memcpy(ch->ls_x, x, sizeof(double) * n);
+    memcpy(ch->ls_g, g, sizeof(double) * n);
+    ch->ls_f = *f;
+    ch->ls_cache_valid = 1;
     return 0;
 }
 
@@ -514,9 +534,18 @@ static int ofw_local_search(Chain *ch, const double *x_in, double *x_out, double
     int nit = 0, nfev = 0;
     ch->in_ls = 1;
     ch->n_ls += 1;
+    ch->ls_cache_valid = 0;
     int warnflag = orc_lbfgsb_minimize(n, ch->p->lower, ch->p->upper, x_out, e_out,
                                        fun_and_grad, ch, &o, &nit, &nfev);
     ch->in_ls = 0;
+    if (getenv("ORC_TRACE_LS")) {
+        fprintf(stderr, "LSX");
+        for (int i = 0; i < n; ++i) fprintf(stderr, " %.17g", x_in[i]);
+        fprintf(stderr, "\n");
+    }
+    if (getenv("ORC_TRACE_LS"))
+        fprintf(stderr, "LS ncall=%lld warn=%d nit=%d nfev=%d e=%.17g\n", (long long)ch->nb_fun_call,
+                warnflag, nit, nfev, *e_out);
     if (warnflag != 0) {                       /* not mres.success -> (BIG_VALUE, None) */
         *e_out = BIG_VALUE;
         return 0;
@@ -573,10 +602,11 @@ static int run_chain(const OrcProblem *p, const OrcConfig *c, int64_t chain, con
     Chain ch;
     memset(&ch, 0, sizeof(ch));
     ch.p = p; ch.c = c; ch.dim = dim;
-    double *buf = (double *)calloc((size_t)dim * 8, sizeof(double));
+    double *buf = (double *)calloc((size_t)dim * 10, sizeof(double));
     if (!buf) return -3;
     ch.x_cur = buf; ch.xbest = buf + dim; ch.xmin = buf + 2 * dim; ch.x_visit = buf + 3 * dim;
     ch.visits = buf + 4 * dim; ch.gx1 = buf + 5 * dim; ch.gx2 = buf + 6 * dim;
+    ch.ls_x = buf + 8 * dim; ch.ls_g = buf + 9 * dim;
     double *xls = buf + 7 * dim;
     ch.rng.mode = c->rng_mode;
     if (c->rng_mode == ORC_RNG_TAPE) {
@@ -759,9 +789,10 @@ int orc_local_search(const OrcProblem *p, const double *x_in, double *x_out, dou
                      int64_t *nfev, int64_t *nit)
 {
     Chain ch; OrcConfig c;
-    double *scratch = (double *)calloc((size_t)p->dim * 2, sizeof(double));
+    double *scratch = (double *)calloc((size_t)p->dim * 4, sizeof(double));
     hook_chain(&ch, p, &c, NULL, 0, NULL);
     ch.gx1 = scratch; ch.gx2 = scratch + p->dim;
+    ch.ls_x = scratch + 2 * p->dim; ch.ls_g = scratch + 3 * p->dim;
     (void)hook_fg;
     int ok = ofw_local_search(&ch, x_in, x_out, f_out);
     if (nfev) *nfev = ch.nb_fun_call;

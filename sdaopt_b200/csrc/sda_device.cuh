@@ -1,0 +1,184 @@
+// sda_device.cuh -- device building blocks of the dual-annealing hot path (sm_100a).
+//
+// Mapping: ONE CHAIN PER WARP.  Coordinates are striped over the 32 lanes (coordinate k lives in
+// lane k & 31), chain vectors live in shared memory, scalars (energies, counters) are replicated
+// in the registers of every lane and stay warp-uniform, reductions are xor-butterflies so every
+// lane ends with the same bits.
+//
+// Reference citations are to /root/reference/sdaopt/_sda.py unless another file is named.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sdaopt_b200.h"
+
+#define SDA_WARP 32
+#define SDA_FULL_MASK 0xffffffffu
+
+namespace sda {
+
+constexpr double kBigValue = 1e16;        // BIG_VALUE            :17
+constexpr double kTailLimit = 1.e8;       // tail_limit           :27
+constexpr double kMinVisitBound = 1.e-10; // min_visit_bound      :28
+constexpr int kMaxReinit = 1000;          // MAX_REINIT_COUNT     :116
+constexpr double kTwoPi = 6.283185307179586476925286766559;  // 2*np.pi rounds to this double
+constexpr double kPi = 3.141592653589793238462643383279;
+
+enum Purpose : uint32_t { kPolar = 0, kClip = 1, kAccept = 2, kInit = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Counter-based: any draw is addressable, so
+// the lanes of a warp sample their coordinates independently (K2).
+// ---------------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                          uint32_t (&o)[4]) const
+    {
+        uint32_t a0 = k0, a1 = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ a0;
+            c1 = lo1;
+            c2 = hi0 ^ c3 ^ a1;
+            c3 = lo0;
+            a0 += 0x9E3779B9u;
+            a1 += 0xBB67AE85u;
+        }
+        o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+    }
+};
+
+// numpy RandomState.random_sample() construction (genrand_res53)
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b)
+{
+    // (a>>5)*2^26 + (b>>6) < 2^53 is exact in double; the division by 2^53 is a power-of-two scale
+    return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * 1.1102230246251565e-16;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions: every lane receives bit-identical results
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SDA_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_prod(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(SDA_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(SDA_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(SDA_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_bcast(double v, int src)
+{
+    return __shfl_sync(SDA_FULL_MASK, v, src);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: visiting distribution.  The arithmetic follows the reference operation by operation with
+// explicit round-to-nearest intrinsics (no FMA contraction) so that the only differences from
+// the reference are the last-bit differences of log/exp themselves.
+// ---------------------------------------------------------------------------------------------
+struct VisitConst {
+    double sigmax;   // sigmax(T), K1 table                               :76-86
+    double qv_m1;    // qv - 1.0
+    double three_mq; // 3.0 - qv
+};
+
+// gaussian_fn(1) / gaussian_fn(0) + visit_fn from one accepted polar pair   :87-91, :103-107
+__device__ __forceinline__ double visit_from_polar(double xg, double yg, double s,
+                                                   const VisitConst &vc)
+{
+    const double root = sqrt(__dmul_rn(__ddiv_rn(-2.0, s), log(s)));   // :103-104
+    const double x = __dmul_rn(vc.sigmax, __dmul_rn(root, yg));        // :87, :105
+    const double y = __dmul_rn(root, xg);                              // :88, :107
+    const double den = exp(__ddiv_rn(__dmul_rn(vc.qv_m1, log(fabs(y))), vc.three_mq)); // :89-90
+    return __ddiv_rn(x, den);                                          // :91
+}
+
+// a = x - lower; b = fmod(a, R) + R; x = fmod(b, R) + lower; nudge      :50-55 / :65-72
+__device__ __forceinline__ double wrap_coord(double xv, double lower, double range)
+{
+    const double a = __dsub_rn(xv, lower);
+    const double b = __dadd_rn(fmod(a, range), range);
+    double r = __dadd_rn(fmod(b, range), lower);
+    if (fabs(__dsub_rn(r, lower)) < kMinVisitBound) r = __dadd_rn(r, 1.e-10);
+    return r;
+}
+
+// Uniform sources ------------------------------------------------------------------------------
+// Tape: sequential replay of recorded RandomState draws; every lane walks the same tape.
+struct TapeRng {
+    const double *tape;
+    int64_t pos, len;
+    bool exhausted;
+    __device__ __forceinline__ double next()
+    {
+        if (pos >= len) { exhausted = true; return 0.25; }
+        return tape[pos++];
+    }
+};
+
+// Philox addressing context (see include/sdaopt_b200.h "RNG protocol")
+struct PhiloxRng {
+    Philox ph;
+    uint32_t iter, j;
+    __device__ __forceinline__ void pair(uint32_t purpose, uint32_t k, uint32_t attempt, double &u1,
+                                         double &u2) const
+    {
+        uint32_t o[4];
+        ph.block(k, attempt, (purpose << 24) | j, iter, o);
+        u1 = u53(o[0], o[1]);
+        u2 = u53(o[2], o[3]);
+    }
+};
+
+// one visit_fn(T) draw for coordinate k, Philox source: polar rejection loop        :94-102
+__device__ __forceinline__ double visit_sample_philox(const PhiloxRng &rng, uint32_t k,
+                                                      const VisitConst &vc)
+{
+    double xg, yg, s;
+    uint32_t attempt = 0;
+    do {
+        double u1, u2;
+        rng.pair(kPolar, k, attempt++, u1, u2);
+        xg = __dsub_rn(__dmul_rn(u1, 2.0), 1.0);
+        yg = __dsub_rn(__dmul_rn(u2, 2.0), 1.0);
+        s = __dadd_rn(__dmul_rn(xg, xg), __dmul_rn(yg, yg));
+    } while (s <= 0.0 || s >= 1.0);
+    return visit_from_polar(xg, yg, s, vc);
+}
+
+// same from the tape (uniform across the warp)
+__device__ __forceinline__ double visit_sample_tape(TapeRng &rng, const VisitConst &vc)
+{
+    double xg, yg, s;
+    do {
+        const double u1 = rng.next();
+        const double u2 = rng.next();
+        if (rng.exhausted) return 0.0;
+        xg = __dsub_rn(__dmul_rn(u1, 2.0), 1.0);
+        yg = __dsub_rn(__dmul_rn(u2, 2.0), 1.0);
+        s = __dadd_rn(__dmul_rn(xg, xg), __dmul_rn(yg, yg));
+    } while (s <= 0.0 || s >= 1.0);
+    return visit_from_polar(xg, yg, s, vc);
+}
+
+}  // namespace sda

@@ -1,0 +1,737 @@
+// sda_kernels.cu -- kernels and the C ABI of libsdaopt_b200.so (include/sdaopt_b200.h).
+//
+// One persistent launch per batch: every warp pulls chain indices from a device-side counter and
+// runs whole chains (SDARunner.search, _sda.py:393-418) start to finish, including the local
+// searches, so heavy-tailed run lengths (suite early exits, L-BFGS-B) balance dynamically and no
+// host round trip happens between temperature steps.
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "sda_chain.cuh"
+#include "sda_lbfgsb.cuh"
+
+namespace sda {
+
+// MarkovChain.local_search                                                        :236-273
+__device__ inline void markov_local_search(const DeviceArgs &a, ChainState &st, LsWork &w,
+                                           double *x_cur, double *x_vis, const double *lo,
+                                           const double *up, double *xbest, double *xmin, int lane)
+{
+    const int dim = a.dim;
+    double e;
+    if (st.state_improved) {
+        ofw_local_search(a, st, w, xbest, x_vis, lo, up, e, lane);
+        if (st.stop) return;
+        if (e < st.ebest) {
+            st.not_improved_idx = 0;
+            st.ebest = e;
+            copy_vec(xbest, w.x, dim, lane);
+            st.e_cur = e;
+            copy_vec(x_cur, w.x, dim, lane);
+            __syncwarp();
+            return;
+        }
+    }
+    // :254-258 is dead code in the reference (K = 100*D is never < 90*D): no uniform is drawn
+    if (st.not_improved_idx >= st.not_improved_max_idx) {
+        const int ok = ofw_local_search(a, st, w, xmin, x_vis, lo, up, e, lane);
+        if (st.stop) return;
+        if (ok) copy_vec(xmin, w.x, dim, lane);
+        st.emin = e;
+        st.not_improved_idx = 0;
+        st.not_improved_max_idx = dim;
+        if (e < st.ebest) {
+            st.ebest = st.emin;
+            copy_vec(xbest, w.x, dim, lane);
+            st.e_cur = e;
+            copy_vec(x_cur, w.x, dim, lane);
+        }
+        __syncwarp();
+    }
+}
+
+// SDARunner.__init__ + search + result for one chain                               :357-428
+template <bool TAPE>
+__device__ inline void run_chain(const DeviceArgs &a, long long chain, double *x_cur, double *x_vis,
+                                 double *sv, const double *lo, const double *up, double *ls_slot,
+                                 int lane)
+{
+    const int dim = a.dim;
+    ChainState st;
+    st.e_cur = st.ebest = st.emin = 0.0;
+    st.not_improved_idx = 0; st.not_improved_max_idx = 1000;     // :186-187
+    st.ncall = st.ncall_ls = st.n_ls = 0;
+    st.mon_calls = 0; st.ncall_hit = a.max_calls;                // bench.py:269
+    st.f_hit = __longlong_as_double(0x7ff0000000000000LL);       // bench.py:272
+    st.trace_pos = 0;
+    st.state_improved = 0; st.stop = 0; st.hit = 0; st.status = 0; st.have_best = 0;
+
+    Rng<TAPE> rng;
+    if constexpr (TAPE) {
+        rng.t.tape = a.tape + chain * a.tape_len;
+        rng.t.pos = 0; rng.t.len = a.tape_len; rng.t.exhausted = false;
+    } else {
+        const unsigned long long s = a.seeds ? a.seeds[chain] : (unsigned long long)chain;
+        rng.p.ph.k0 = (uint32_t)s; rng.p.ph.k1 = (uint32_t)(s >> 32);
+        rng.p.iter = 0; rng.p.j = 0xFFFFFFu;
+    }
+    double *xbest = a.out.x + chain * dim;
+    double *xmin = a.xmin + chain * dim;
+    LsWork w;
+    w.bind(ls_slot, dim);
+
+    int err = energy_reset<TAPE>(a, st, rng, x_cur, lo, up,
+                                 a.x0 ? a.x0 + chain * dim : nullptr, xbest, lane);
+    long long iter = 0;
+    if (!err && !st.stop) {
+        st.emin = st.e_cur;                                      // :176-177
+        copy_vec(xmin, x_cur, dim, lane);
+        bool max_steps_reached = false;
+        while (!max_steps_reached && !st.stop && !err) {
+            if constexpr (TAPE) { if (rng.t.exhausted) break; }
+            for (long long i = 0; i < a.maxiter; ++i) {
+                double temperature, sigmax;
+                if (i < a.table_len) { temperature = a.temp_table[i]; sigmax = a.sigmax_table[i]; }
+                else { temperature = a.temp_table[a.table_len - 1]; sigmax = a.sigmax_table[a.table_len - 1]; }
+                iter += 1;
+                if constexpr (!TAPE) { rng.p.iter = (uint32_t)iter; rng.p.j = 0xFFFFFFu; }
+                if (iter == a.maxiter) { max_steps_reached = true; break; }          // :404-406
+                if (temperature < a.temperature_restart) {                             // :408-410
+                    err = energy_reset<TAPE>(a, st, rng, x_cur, lo, up, nullptr, xbest, lane);
+                    break;
+                }
+                markov_run<TAPE>(a, st, rng, chain, i, temperature, sigmax, x_cur, x_vis, sv, lo,
+                                 up, xbest, xmin, lane);                               // :412
+                if (st.stop) break;
+                if constexpr (TAPE) { if (rng.t.exhausted) break; }
+                if ((double)st.ncall >= a.maxfun) break;                               // :413-414
+                if (!a.pure_sa) {                                                      // :415-418
+                    markov_local_search(a, st, w, x_cur, x_vis, lo, up, xbest, xmin, lane);
+                    if (st.stop) break;
+                    if ((double)st.ncall >= a.maxfun) break;
+                }
+            }
+            if (a.maxiter <= 0) break;
+        }
+    }
+    if constexpr (TAPE) { if (rng.t.exhausted) err |= SDA_CHAIN_TAPE_EXHAUSTED; }
+    __syncwarp();
+    if (lane == 0) {
+        a.out.fun[chain] = st.ebest;
+        a.out.nit[chain] = iter;
+        a.out.ncall[chain] = st.ncall;
+        a.out.status[chain] = err;
+        if (a.out.ncall_ls) a.out.ncall_ls[chain] = st.ncall_ls;
+        if (a.out.n_ls) a.out.n_ls[chain] = st.n_ls;
+        if (a.out.hit) a.out.hit[chain] = st.hit;
+        if (a.out.ncall_hit) a.out.ncall_hit[chain] = st.ncall_hit;
+        if (a.out.f_hit) a.out.f_hit[chain] = st.f_hit;
+        if constexpr (TAPE) { if (a.out.tape_used) a.out.tape_used[chain] = rng.t.pos; }
+        else { if (a.out.tape_used) a.out.tape_used[chain] = 0; }
+    }
+}
+
+// shared memory: lower[D] upper[D] | per warp: x_cur[D] x_vis[D] sv[D]
+template <bool TAPE>
+__global__ void __launch_bounds__(256) sda_anneal_kernel(const DeviceArgs a)
+{
+    extern __shared__ double smem[];
+    const int dim = a.dim;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    double *lo = smem;
+    double *up = smem + dim;
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) { lo[k] = a.lower[k]; up[k] = a.upper[k]; }
+    __syncthreads();
+    double *x_cur = smem + 2 * dim + (size_t)warp * 3 * dim;
+    double *x_vis = x_cur + dim;
+    double *sv = x_vis + dim;
+    const long long slot = (long long)blockIdx.x * warps_per_block + warp;
+    double *ls_slot = a.ls_work ? a.ls_work + slot * a.ls_stride : nullptr;
+    for (;;) {
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(a.work_counter, 1ULL);
+        c = __shfl_sync(SDA_FULL_MASK, c, 0);
+        if ((long long)c >= a.n_chains) break;
+        run_chain<TAPE>(a, (long long)c, x_cur, x_vis, sv, lo, up, ls_slot, lane);
+        __syncwarp();
+    }
+}
+
+// objective evaluation at n points, one warp per point
+__global__ void __launch_bounds__(256) sda_eval_kernel(int functor, int dim, const double *params,
+                                                       const double *x, long long n, double *f)
+{
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = wid; p < n; p += nw) {
+        const double v = eval_objective(functor, x + p * dim, dim, params, lane);
+        if (lane == 0) f[p] = v;
+    }
+}
+
+// VisitingDistribution.visiting on a tape (unit-test hook)                           :40-73
+__global__ void sda_visiting_kernel(DeviceArgs a, const double *x, long long step, double sigmax,
+                                    double *x_visit, long long *tape_used)
+{
+    extern __shared__ double smem[];
+    const int dim = a.dim, lane = threadIdx.x & 31;
+    double *sv = smem;
+    TapeRng rng = { a.tape, 0, a.tape_len, false };
+    const VisitConst vc = { sigmax, a.qv - 1.0, 3.0 - a.qv };
+    if (step < dim) {
+        for (int k = 0; k < dim; ++k) {
+            const double v = visit_sample_tape(rng, vc);
+            if ((k & 31) == lane) sv[k] = v;
+        }
+        const double us = rng.next(), ls = rng.next();
+        __syncwarp();
+        for (int k = lane; k < dim; k += SDA_WARP) {
+            double v = sv[k];
+            if (v > kTailLimit) v = __dmul_rn(kTailLimit, us);
+            else if (v < -kTailLimit) v = __dmul_rn(-kTailLimit, ls);
+            x_visit[k] = wrap_coord(__dadd_rn(v, x[k]), a.lower[k], __dsub_rn(a.upper[k], a.lower[k]));
+        }
+    } else {
+        const int index = (int)(step - dim);
+        for (int k = lane; k < dim; k += SDA_WARP) x_visit[k] = x[k];
+        double visit = visit_sample_tape(rng, vc);
+        if (visit > kTailLimit) visit = __dmul_rn(kTailLimit, rng.next());
+        else if (visit < -kTailLimit) visit = __dmul_rn(-kTailLimit, rng.next());
+        __syncwarp();
+        if (lane == 0)
+            x_visit[index] = wrap_coord(__dadd_rn(visit, x[index]), a.lower[index],
+                                        __dsub_rn(a.upper[index], a.lower[index]));
+    }
+    if (lane == 0) *tape_used = rng.exhausted ? -1 : rng.pos;
+}
+
+// n successive visit_fn(T) values from a tape (unit-test hook)                       :75-91
+__global__ void sda_visit_fn_kernel(double qv, double sigmax, const double *tape, long long tape_len,
+                                    double *out, long long n, long long *tape_used)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    TapeRng rng = { tape, 0, tape_len, false };
+    const VisitConst vc = { sigmax, qv - 1.0, 3.0 - qv };
+    for (long long i = 0; i < n; ++i) out[i] = visit_sample_tape(rng, vc);
+    *tape_used = rng.exhausted ? -1 : rng.pos;
+}
+
+// ObjectiveFunWrapper.local_search for n start points, one warp each (unit-test hook) :347-351
+__global__ void __launch_bounds__(128) sda_local_search_kernel(DeviceArgs a, const double *x_in,
+                                                              long long n, double *x_out,
+                                                              double *f_out, int *success,
+                                                              long long *nfev)
+{
+    extern __shared__ double smem[];
+    const int dim = a.dim;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double *lo = smem, *up = smem + dim;
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) { lo[k] = a.lower[k]; up[k] = a.upper[k]; }
+    __syncthreads();
+    double *xe = smem + 2 * dim + (size_t)warp * dim;
+    const long long slot = (long long)blockIdx.x * wpb + warp;
+    const long long nslots = (long long)gridDim.x * wpb;
+    LsWork w;
+    w.bind(a.ls_work + slot * a.ls_stride, dim);
+    for (long long p = slot; p < n; p += nslots) {
+        ChainState st;
+        memset(&st, 0, sizeof(st));
+        double e;
+        const int ok = ofw_local_search(a, st, w, x_in + p * dim, xe, lo, up, e, lane);
+        for (int k = lane; k < dim; k += SDA_WARP) x_out[p * dim + k] = w.x[k];
+        if (lane == 0) { f_out[p] = e; success[p] = ok; nfev[p] = st.ncall; }
+        __syncwarp();
+    }
+}
+
+// FP64 FMA throughput probe: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) sda_dfma_kernel(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace sda
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using sda::DeviceArgs;
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return SDA_E_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
+    } while (0)
+
+static const char *kFunctorNames[SDA_FN_COUNT] = {
+    "Rastrigin", "ShiftedRastrigin", "Rosenbrock", "Ackley01", "Schwefel01", "Schwefel26",
+    "Exponential", "SuttonChen", "Constant", "Sphere", "Griewank"};
+
+extern "C" int sda_abi_version(void) { return SDA_ABI_VERSION; }
+
+extern "C" const char *sda_error_string(int code)
+{
+    switch (code) {
+    case SDA_OK: return "ok";
+    case SDA_E_INVALID: return "invalid argument";
+    case SDA_E_BOUNDS: return "Bounds are note consistent min < max";
+    case SDA_E_CUDA: return "CUDA error (see sda_last_cuda_error)";
+    case SDA_E_WORKSPACE: return "workspace too small";
+    case SDA_E_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *sda_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" int sda_functor_id(const char *name)
+{
+    if (!name) return SDA_E_INVALID;
+    for (int i = 0; i < SDA_FN_COUNT; ++i)
+        if (strcmp(name, kFunctorNames[i]) == 0) return i;
+    return SDA_E_INVALID;
+}
+
+extern "C" const char *sda_functor_name(int functor)
+{
+    if (functor < 0 || functor >= SDA_FN_COUNT) return NULL;
+    return kFunctorNames[functor];
+}
+
+extern "C" int sda_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+// ---- K1 on the host, the reference's formulas with libm                     :396-402, :76-86
+static double host_temperature(double t0, double qv, long long i)
+{
+    const double t1 = exp((qv - 1) * log(2.0)) - 1.0;
+    const double s = (double)i + 2.0;
+    const double t2 = exp((qv - 1) * log(s)) - 1.0;
+    return t0 * t1 / t2;
+}
+static double host_sigmax(double temperature, double qv)
+{
+    const double factor1 = exp(log(temperature) / (qv - 1.0));
+    const double factor2 = exp((4.0 - qv) * log(qv - 1.0));
+    const double factor3 = exp((2.0 - qv) * log(2.0) / (qv - 1.0));
+    const double factor4 = sqrt(M_PI) * factor1 * factor2 / (factor3 * (3.0 - qv));
+    const double factor5 = 1.0 / (qv - 1.0) - 0.5;
+    const double d1 = 2.0 - factor5;
+    const double factor6 = M_PI * (1.0 - factor5) / sin(M_PI * (1.0 - factor5)) / exp(lgamma(d1));
+    return exp(-(qv - 1.0) * log(factor6 / factor4) / (3.0 - qv));
+}
+
+// number of K1 table entries the device needs: up to and including the first T < T_restart
+static long long table_entries(const SdaConfig *c)
+{
+    if (c->temp_table && c->sigmax_table && c->table_len > 0) return c->table_len;
+    long long n = 0;
+    for (long long i = 0; i < c->maxiter; ++i) {
+        ++n;
+        if (host_temperature(c->initial_temp, c->visit, i) < c->temperature_restart) break;
+    }
+    return n > 0 ? n : 1;
+}
+
+struct LaunchPlan {
+    int warps_per_block, blocks;
+    size_t smem;
+    long long slots;
+};
+
+static int plan_launch(int dim, long long n_chains, LaunchPlan *lp)
+{
+    int dev = 0, sms = 0, smem_max = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    int wpb = 8;
+    while (wpb > 1 && (size_t)(2 + 3 * wpb) * dim * sizeof(double) > (size_t)smem_max) wpb >>= 1;
+    size_t smem = (size_t)(2 + 3 * wpb) * dim * sizeof(double);
+    if (smem > (size_t)smem_max) return SDA_E_UNSUPPORTED;
+    // resident blocks per SM: bounded by shared memory and by 2048 threads
+    int bps = (int)((size_t)(smem_max) / (smem + 1024));
+    if (bps < 1) bps = 1;
+    int max_bps = 64 / wpb; // 64 warps per SM
+    if (max_bps > 4) max_bps = 4; // register budget: 4 x 256 threads
+    if (bps > max_bps) bps = max_bps;
+    long long want = (n_chains + wpb - 1) / wpb;
+    long long blocks = (long long)sms * bps;
+    if (blocks > want) blocks = want;
+    if (blocks < 1) blocks = 1;
+    lp->warps_per_block = wpb;
+    lp->blocks = (int)blocks;
+    lp->smem = smem;
+    lp->slots = blocks * wpb;
+    return SDA_OK;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// workspace layout: [counter 256B][temp table][sigmax table][xmin C*D][ls slots]
+static size_t workspace_layout(const SdaProblem *p, const SdaConfig *c, long long n_chains,
+                               long long slots, size_t *off_temp, size_t *off_sig, size_t *off_xmin,
+                               size_t *off_ls, long long *ls_stride)
+{
+    const long long tn = table_entries(c);
+    size_t off = 256;
+    *off_temp = off; off += align256((size_t)tn * sizeof(double));
+    *off_sig = off; off += align256((size_t)tn * sizeof(double));
+    *off_xmin = off; off += align256((size_t)n_chains * p->dim * sizeof(double));
+    *off_ls = off;
+    *ls_stride = (sda::ls_workspace_doubles(p->dim) + 31) & ~31LL;
+    if (!c->pure_sa) off += align256((size_t)slots * (size_t)*ls_stride * sizeof(double));
+    return off;
+}
+
+static int max_slots(void)
+{
+    // upper bound used for workspace sizing without touching the device: 160 SMs x 32 warps
+    return 160 * 32;
+}
+
+extern "C" size_t sda_workspace_bytes(const SdaProblem *p, const SdaConfig *c, int64_t n_chains)
+{
+    if (!p || !c || p->dim <= 0 || n_chains <= 0) return 0;
+    size_t a, b, d, e;
+    long long s;
+    return workspace_layout(p, c, n_chains, max_slots(), &a, &b, &d, &e, &s);
+}
+
+static int validate(const SdaProblem *p, const SdaConfig *c, int64_t n_chains)
+{
+    if (!p || !c || p->dim <= 0 || n_chains <= 0) return SDA_E_INVALID;
+    if (p->functor < 0 || p->functor >= SDA_FN_COUNT) return SDA_E_INVALID;
+    if (c->rng_mode != SDA_RNG_PHILOX && c->rng_mode != SDA_RNG_TAPE) return SDA_E_INVALID;
+    if (p->functor == SDA_FN_SUTTON_CHEN && p->dim % 3 != 0) return SDA_E_INVALID;
+    if ((p->functor == SDA_FN_SHIFTED_RASTRIGIN || p->functor == SDA_FN_CONSTANT) &&
+        (p->params == NULL || p->n_params < 1))
+        return SDA_E_INVALID;
+    return SDA_OK;
+}
+
+extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_chains,
+                             const double *x0, const uint64_t *seeds, const double *tape,
+                             int64_t tape_len, const SdaResult *out, void *workspace,
+                             size_t workspace_bytes, void *stream_)
+{
+    int rc = validate(p, c, n_chains);
+    if (rc) return rc;
+    if (!out || !out->x || !out->fun || !out->nit || !out->ncall || !out->status || !workspace)
+        return SDA_E_INVALID;
+    if (c->rng_mode == SDA_RNG_TAPE && (!tape || tape_len <= 0)) return SDA_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LaunchPlan lp;
+    rc = plan_launch(p->dim, n_chains, &lp);
+    if (rc) return rc;
+    size_t off_temp, off_sig, off_xmin, off_ls;
+    long long ls_stride;
+    const size_t need = workspace_layout(p, c, n_chains, lp.slots, &off_temp, &off_sig, &off_xmin,
+                                         &off_ls, &ls_stride);
+    if (need > workspace_bytes) return SDA_E_WORKSPACE;
+    char *ws = (char *)workspace;
+
+    // K1 tables (host) -> device
+    const long long tn = table_entries(c);
+    std::vector<double> tt((size_t)tn), st((size_t)tn);
+    if (c->temp_table && c->sigmax_table && c->table_len > 0) {
+        memcpy(tt.data(), c->temp_table, (size_t)tn * sizeof(double));
+        memcpy(st.data(), c->sigmax_table, (size_t)tn * sizeof(double));
+    } else {
+        for (long long i = 0; i < tn; ++i) {
+            tt[(size_t)i] = host_temperature(c->initial_temp, c->visit, i);
+            st[(size_t)i] = host_sigmax(tt[(size_t)i], c->visit);
+        }
+    }
+    CK(cudaMemcpyAsync(ws + off_temp, tt.data(), (size_t)tn * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(ws + off_sig, st.data(), (size_t)tn * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(ws, 0, 256, stream));
+    // tt/st are pageable: cudaMemcpyAsync has staged them before it returned, so they may die here
+
+    DeviceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.functor = p->functor; a.dim = p->dim;
+    a.lower = p->lower; a.upper = p->upper; a.params = p->params;
+    a.maxiter = c->maxiter; a.initial_temp = c->initial_temp; a.qv = c->visit; a.qa = c->accept;
+    a.maxfun = c->maxfun; a.temperature_restart = c->temperature_restart; a.pure_sa = c->pure_sa;
+    a.max_calls = c->max_calls; a.fglob_tol = c->fglob + c->tol; a.trace_len = c->trace_len;
+    a.temp_table = (const double *)(ws + off_temp);
+    a.sigmax_table = (const double *)(ws + off_sig);
+    a.table_len = tn;
+    a.n_chains = n_chains; a.x0 = x0; a.seeds = (const unsigned long long *)seeds;
+    a.tape = tape; a.tape_len = tape_len;
+    a.out = *out;
+    if (c->trace_len <= 0) { a.out.trace_e = NULL; a.out.trace_d = NULL; }
+    a.xmin = (double *)(ws + off_xmin);
+    a.ls_work = c->pure_sa ? NULL : (double *)(ws + off_ls);
+    a.ls_stride = ls_stride;
+    a.work_counter = (unsigned long long *)ws;
+    int lsmax = p->dim * 6;
+    if (lsmax < 100) lsmax = 100;
+    if (lsmax > 1000) lsmax = 1000;
+    a.ls_maxiter = lsmax;
+
+    const int threads = lp.warps_per_block * 32;
+    if (c->rng_mode == SDA_RNG_TAPE) {
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        sda::sda_anneal_kernel<true><<<lp.blocks, threads, lp.smem, stream>>>(a);
+    } else {
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        sda::sda_anneal_kernel<false><<<lp.blocks, threads, lp.smem, stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    return SDA_OK;
+}
+
+// ---- small RAII helper for the host-pointer entry points -----------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+    cudaError_t upload(const void *h, size_t bytes)
+    {
+        cudaError_t e = alloc(bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+    }
+};
+
+static int upload_problem(const SdaProblem *p, SdaProblem *dp, DevBuf &lo, DevBuf &up, DevBuf &pa)
+{
+    for (int k = 0; k < p->dim; ++k)
+        if (!(p->lower[k] < p->upper[k])) return SDA_E_BOUNDS;          // _sda.py:366-367
+    CK(lo.upload(p->lower, sizeof(double) * p->dim));
+    CK(up.upload(p->upper, sizeof(double) * p->dim));
+    *dp = *p;
+    dp->lower = (const double *)lo.p;
+    dp->upper = (const double *)up.p;
+    dp->params = NULL;
+    if (p->params && p->n_params > 0) {
+        CK(pa.upload(p->params, sizeof(double) * p->n_params));
+        dp->params = (const double *)pa.p;
+    }
+    return SDA_OK;
+}
+
+extern "C" int sda_batch_run_host(const SdaProblem *p, const SdaConfig *c, int64_t n_chains,
+                                  const double *x0, const uint64_t *seeds, const double *tape,
+                                  int64_t tape_len, const SdaResult *out, int device)
+{
+    int rc = validate(p, c, n_chains);
+    if (rc) return rc;
+    if (!p->lower || !p->upper || !out) return SDA_E_INVALID;
+    CK(cudaSetDevice(device));
+    const size_t C = (size_t)n_chains, D = (size_t)p->dim;
+    DevBuf lo, up, pa, dx0, dseeds, dtape, ws;
+    SdaProblem dp;
+    rc = upload_problem(p, &dp, lo, up, pa);
+    if (rc) return rc;
+    if (x0) CK(dx0.upload(x0, C * D * sizeof(double)));
+    if (seeds) CK(dseeds.upload(seeds, C * sizeof(uint64_t)));
+    if (tape && c->rng_mode == SDA_RNG_TAPE) CK(dtape.upload(tape, C * (size_t)tape_len * sizeof(double)));
+    const size_t tl = c->trace_len > 0 ? (size_t)c->trace_len : 0;
+    // one device block for all outputs
+    DevBuf ox, ofun, onit, oncall, oncls, onls, ostat, ohit, onhit, ofhit, ote, otd, otu;
+    CK(ox.alloc(C * D * 8)); CK(ofun.alloc(C * 8)); CK(onit.alloc(C * 8)); CK(oncall.alloc(C * 8));
+    CK(oncls.alloc(C * 8)); CK(onls.alloc(C * 8)); CK(ostat.alloc(C * 4)); CK(ohit.alloc(C * 4));
+    CK(onhit.alloc(C * 8)); CK(ofhit.alloc(C * 8)); CK(otu.alloc(C * 8));
+    if (tl) { CK(ote.alloc(C * tl * 8)); CK(otd.alloc(C * tl)); CK(cudaMemset(ote.p, 0, C * tl * 8)); CK(cudaMemset(otd.p, 0, C * tl)); }
+    SdaResult dout;
+    dout.x = (double *)ox.p; dout.fun = (double *)ofun.p; dout.nit = (int64_t *)onit.p;
+    dout.ncall = (int64_t *)oncall.p; dout.ncall_ls = (int64_t *)oncls.p; dout.n_ls = (int64_t *)onls.p;
+    dout.status = (int32_t *)ostat.p; dout.hit = (int32_t *)ohit.p; dout.ncall_hit = (int64_t *)onhit.p;
+    dout.f_hit = (double *)ofhit.p; dout.trace_e = tl ? (double *)ote.p : NULL;
+    dout.trace_d = tl ? (uint8_t *)otd.p : NULL; dout.tape_used = (int64_t *)otu.p;
+    const size_t wbytes = sda_workspace_bytes(&dp, c, n_chains);
+    CK(ws.alloc(wbytes));
+    rc = sda_batch_run(&dp, c, n_chains, (const double *)dx0.p, (const uint64_t *)dseeds.p,
+                       (const double *)dtape.p, tape_len, &dout, ws.p, wbytes, NULL);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+#define DL(field, dev, bytes) \
+    if (out->field) CK(cudaMemcpy(out->field, dev.p, bytes, cudaMemcpyDeviceToHost))
+    DL(x, ox, C * D * 8); DL(fun, ofun, C * 8); DL(nit, onit, C * 8); DL(ncall, oncall, C * 8);
+    DL(ncall_ls, oncls, C * 8); DL(n_ls, onls, C * 8); DL(status, ostat, C * 4); DL(hit, ohit, C * 4);
+    DL(ncall_hit, onhit, C * 8); DL(f_hit, ofhit, C * 8); DL(tape_used, otu, C * 8);
+    if (tl) { DL(trace_e, ote, C * tl * 8); DL(trace_d, otd, C * tl); }
+#undef DL
+    return SDA_OK;
+}
+
+extern "C" int sda_eval(const SdaProblem *p, const double *x, int64_t n, double *f, void *stream)
+{
+    if (!p || !x || !f || n <= 0 || p->dim <= 0) return SDA_E_INVALID;
+    if (p->functor < 0 || p->functor >= SDA_FN_COUNT) return SDA_E_INVALID;
+    long long blocks = (n + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    sda::sda_eval_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p->functor, p->dim, p->params, x, n, f);
+    CK(cudaGetLastError());
+    return SDA_OK;
+}
+
+extern "C" int sda_eval_host(const SdaProblem *p, const double *x, int64_t n, double *f, int device)
+{
+    if (!p || !x || !f || n <= 0 || p->dim <= 0) return SDA_E_INVALID;
+    CK(cudaSetDevice(device));
+    DevBuf dx, df, pa;
+    SdaProblem dp = *p;
+    if (p->params && p->n_params > 0) { CK(pa.upload(p->params, sizeof(double) * p->n_params)); dp.params = (const double *)pa.p; }
+    CK(dx.upload(x, (size_t)n * p->dim * sizeof(double)));
+    CK(df.alloc((size_t)n * sizeof(double)));
+    int rc = sda_eval(&dp, (const double *)dx.p, n, (double *)df.p, NULL);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(f, df.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    return SDA_OK;
+}
+
+extern "C" int sda_visiting_host(const SdaProblem *p, double qv, const double *x, int64_t step,
+                                 double temperature, double sigmax, const double *tape,
+                                 int64_t tape_len, double *x_visit, int64_t *tape_used, int device)
+{
+    (void)temperature;
+    if (!p || !x || !tape || !x_visit || p->dim <= 0 || tape_len <= 0) return SDA_E_INVALID;
+    CK(cudaSetDevice(device));
+    DevBuf lo, up, pa, dx, dt, dv, du;
+    SdaProblem dp;
+    int rc = upload_problem(p, &dp, lo, up, pa);
+    if (rc) return rc;
+    CK(dx.upload(x, sizeof(double) * p->dim));
+    CK(dt.upload(tape, sizeof(double) * (size_t)tape_len));
+    CK(dv.alloc(sizeof(double) * p->dim));
+    CK(du.alloc(8));
+    DeviceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dim = p->dim; a.lower = dp.lower; a.upper = dp.upper; a.qv = qv;
+    a.tape = (const double *)dt.p; a.tape_len = tape_len;
+    sda::sda_visiting_kernel<<<1, 32, sizeof(double) * p->dim>>>(a, (const double *)dx.p, step, sigmax,
+                                                                  (double *)dv.p, (long long *)du.p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(x_visit, dv.p, sizeof(double) * p->dim, cudaMemcpyDeviceToHost));
+    if (tape_used) CK(cudaMemcpy(tape_used, du.p, 8, cudaMemcpyDeviceToHost));
+    return SDA_OK;
+}
+
+extern "C" int sda_visit_fn_host(double qv, double sigmax, const double *tape, int64_t tape_len,
+                                 double *out, int64_t n, int64_t *tape_used, int device)
+{
+    if (!tape || !out || n <= 0 || tape_len <= 0) return SDA_E_INVALID;
+    CK(cudaSetDevice(device));
+    DevBuf dt, dout, du;
+    CK(dt.upload(tape, sizeof(double) * (size_t)tape_len));
+    CK(dout.alloc(sizeof(double) * (size_t)n));
+    CK(du.alloc(8));
+    sda::sda_visit_fn_kernel<<<1, 32>>>(qv, sigmax, (const double *)dt.p, tape_len, (double *)dout.p, n,
+                                        (long long *)du.p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dout.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (tape_used) CK(cudaMemcpy(tape_used, du.p, 8, cudaMemcpyDeviceToHost));
+    return SDA_OK;
+}
+
+extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, int64_t n,
+                                     double *x_out, double *f_out, int32_t *success, int64_t *nfev,
+                                     int device)
+{
+    if (!p || !x_in || !x_out || !f_out || n <= 0 || p->dim <= 0) return SDA_E_INVALID;
+    if (p->functor < 0 || p->functor >= SDA_FN_COUNT) return SDA_E_INVALID;
+    CK(cudaSetDevice(device));
+    DevBuf lo, up, pa, dxi, dxo, dfo, dsu, dnf, dls;
+    SdaProblem dp;
+    int rc = upload_problem(p, &dp, lo, up, pa);
+    if (rc) return rc;
+    const size_t D = (size_t)p->dim;
+    CK(dxi.upload(x_in, (size_t)n * D * 8));
+    CK(dxo.alloc((size_t)n * D * 8)); CK(dfo.alloc((size_t)n * 8)); CK(dsu.alloc((size_t)n * 4));
+    CK(dnf.alloc((size_t)n * 8));
+    int wpb = 4;
+    int smem_max = 0;
+    CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    while (wpb > 1 && (size_t)(2 + wpb) * D * 8 > (size_t)smem_max) wpb >>= 1;
+    const size_t smem = (size_t)(2 + wpb) * D * 8;
+    long long blocks = (n + wpb - 1) / wpb;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const long long stride = (sda::ls_workspace_doubles(p->dim) + 31) & ~31LL;
+    CK(dls.alloc((size_t)blocks * wpb * (size_t)stride * 8));
+    DeviceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.functor = p->functor; a.dim = p->dim; a.lower = dp.lower; a.upper = dp.upper; a.params = dp.params;
+    a.ls_work = (double *)dls.p; a.ls_stride = stride;
+    int lsmax = p->dim * 6;
+    if (lsmax < 100) lsmax = 100;
+    if (lsmax > 1000) lsmax = 1000;
+    a.ls_maxiter = lsmax;
+    CK(cudaFuncSetAttribute(sda::sda_local_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sda::sda_local_search_kernel<<<(int)blocks, wpb * 32, smem>>>(a, (const double *)dxi.p, n, (double *)dxo.p,
+                                                                   (double *)dfo.p, (int *)dsu.p, (long long *)dnf.p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(x_out, dxo.p, (size_t)n * D * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(f_out, dfo.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (success) CK(cudaMemcpy(success, dsu.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (nfev) CK(cudaMemcpy(nfev, dnf.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SDA_OK;
+}
+
+extern "C" int sda_fp64_peak(double *tflops, double *ms_out, int device)
+{
+    if (!tflops) return SDA_E_INVALID;
+    CK(cudaSetDevice(device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+    DevBuf out;
+    CK(out.alloc((size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    sda::sda_dfma_kernel<<<blocks, threads>>>((double *)out.p, 1 << 12);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        sda::sda_dfma_kernel<<<blocks, threads>>>((double *)out.p, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return SDA_OK;
+}

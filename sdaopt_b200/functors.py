@@ -1,0 +1,140 @@
+"""Registered device objectives and the resolution of the reference's ``func`` argument.
+
+The reference takes any Python callable ``f(x, *args)`` (_sda.py:440-444).  The B200 path
+evaluates objectives inside the annealing kernel, so ``func`` must name a device functor:
+
+* a :class:`DeviceFunctor` instance (``Rastrigin()``, ``ShiftedRastrigin(3.14159)`` ...),
+* the bound method ``Benchmark.fun`` of a catalogue class whose name is registered
+  (sdaopt/benchmark/go_benchmark_functions), as the suite passes it (benchmark/bench.py:298-299),
+* the function ``sutton_chen`` (sdaopt/benchmark/suttonchen.py:23), matched by name,
+* or the registered name as a string.
+
+Anything else raises ``TypeError``: there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+# name -> id, identical to include/sdaopt_b200.h (SDA_FN_*)
+FUNCTOR_IDS = dict(Rastrigin=0, ShiftedRastrigin=1, Rosenbrock=2, Ackley01=3, Schwefel01=4,
+                   Schwefel26=5, Exponential=6, SuttonChen=7, Constant=8, Sphere=9, Griewank=10)
+
+# default box and known optimum of the catalogue classes (go_funcs_*.py `__init__`)
+_CATALOGUE = {
+    "Rastrigin": ((-5.12, 5.12), 0.0),      # go_funcs_R.py:80-86
+    "Rosenbrock": ((-30.0, 30.0), 0.0),     # go_funcs_R.py:280-286
+    "Ackley01": ((-35.0, 35.0), 0.0),       # go_funcs_A.py:38-41
+    "Schwefel01": ((-100.0, 100.0), 0.0),   # go_funcs_S.py:324-330
+    "Schwefel26": ((-500.0, 500.0), 0.0),   # go_funcs_S.py:606-611
+    "Exponential": ((-1.0, 1.0), -1.0),     # go_funcs_E.py:296-301
+    "Sphere": ((-5.12, 5.12), 0.0),         # go_funcs_S.py:1149-1154
+    "Griewank": ((-100.0, 100.0), 0.0),     # go_funcs_G.py:160-169
+}
+
+
+class DeviceFunctor(object):
+    """A registered CUDA objective.  Calling it evaluates on the GPU (one point or a batch)."""
+
+    def __init__(self, name, params=(), dimensions=None):
+        if name not in FUNCTOR_IDS:
+            raise KeyError("unknown device functor %r" % (name,))
+        self.name = name
+        self.functor_id = FUNCTOR_IDS[name]
+        self.params = np.ascontiguousarray(params, dtype=np.float64).ravel()
+        self.N = dimensions
+        box, fglob = _CATALOGUE.get(name, (None, float("nan")))
+        self.fglob = fglob
+        self._box = box
+
+    @property
+    def bounds(self):
+        if self._box is None or self.N is None:
+            raise AttributeError("%s has no default bounds" % self.name)
+        return [self._box] * int(self.N)
+
+    def fun(self, x, *args):
+        return self(x)
+
+    def __call__(self, x, *args):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        single = x.ndim == 1
+        pts = x.reshape(1, -1) if single else x
+        out = evaluate(self, pts)
+        return float(out[0]) if single else out
+
+    def __repr__(self):
+        return "DeviceFunctor(%s%s)" % (self.name, "" if not self.params.size else
+                                        ", params=%s" % self.params.tolist())
+
+
+def Rastrigin(dimensions=2): return DeviceFunctor("Rastrigin", dimensions=dimensions)
+def Rosenbrock(dimensions=2): return DeviceFunctor("Rosenbrock", dimensions=dimensions)
+def Ackley01(dimensions=2): return DeviceFunctor("Ackley01", dimensions=dimensions)
+def Schwefel01(dimensions=2): return DeviceFunctor("Schwefel01", dimensions=dimensions)
+def Schwefel26(dimensions=2): return DeviceFunctor("Schwefel26", dimensions=dimensions)
+def Exponential(dimensions=2): return DeviceFunctor("Exponential", dimensions=dimensions)
+def Sphere(dimensions=2): return DeviceFunctor("Sphere", dimensions=dimensions)
+def Griewank(dimensions=2): return DeviceFunctor("Griewank", dimensions=dimensions)
+
+
+def ShiftedRastrigin(shift=3.14159, dimensions=None):
+    """README.md:61-71: sum((x-s)^2 - 10 cos(2 pi (x-s))) + 10 D"""
+    return DeviceFunctor("ShiftedRastrigin", params=[shift], dimensions=dimensions)
+
+
+def SuttonChen(n_atoms=None):
+    """sdaopt/benchmark/suttonchen.py:23-40 (x is the flattened (n_atoms, 3) coordinate array)"""
+    return DeviceFunctor("SuttonChen", dimensions=None if n_atoms is None else 3 * n_atoms)
+
+
+def Constant(value):
+    """f(x) = value; the `weirdfunc` of sdaopt/tests/test_sda.py:34"""
+    return DeviceFunctor("Constant", params=[value])
+
+
+def resolve(func):
+    """Map the reference's ``func`` argument to a DeviceFunctor or raise TypeError."""
+    if isinstance(func, DeviceFunctor):
+        return func
+    if isinstance(func, str):
+        return DeviceFunctor(func)
+    owner = getattr(func, "__self__", None)
+    if owner is not None and getattr(func, "__name__", "") in ("fun", "_funcwrapped"):
+        if isinstance(owner, DeviceFunctor):
+            return owner
+        # Algo._funcwrapped wraps self._k.fun (benchmark/bench.py:298)
+        bench = getattr(owner, "_k", owner)
+        name = type(bench).__name__
+        if name in FUNCTOR_IDS:
+            return DeviceFunctor(name, dimensions=getattr(bench, "N", None))
+    if getattr(func, "__name__", "") == "sutton_chen":
+        return DeviceFunctor("SuttonChen")
+    raise TypeError(
+        "sdaopt_b200 evaluates objectives on the GPU: `func` must be a registered device functor "
+        "(sdaopt_b200.functors), a catalogue Benchmark.fun bound method, `sutton_chen` or a "
+        "registered name -- arbitrary Python callables are not supported (no CPU fallback). "
+        "Got %r" % (func,))
+
+
+def make_problem(functor, lower, upper):
+    """(SdaProblem with HOST pointers, keep-alive tuple)"""
+    lower = np.ascontiguousarray(lower, dtype=np.float64)
+    upper = np.ascontiguousarray(upper, dtype=np.float64)
+    params = functor.params
+    p = _lib.SdaProblem(functor.functor_id, int(lower.size), lower.ctypes.data, upper.ctypes.data,
+                        params.ctypes.data if params.size else None, int(params.size))
+    return p, (lower, upper, params)
+
+
+def evaluate(functor, points, device=0):
+    """Objective values at points[n, D] (replaces Benchmark.fun / sutton_chen per point)."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n, dim = pts.shape
+    dummy = np.zeros(dim)
+    p, keep = make_problem(functor, dummy, dummy + 1)
+    out = np.empty(n, dtype=np.float64)
+    _lib.require_cuda()
+    _lib.check(_lib.lib().sda_eval_host(C.byref(p), pts.ctypes.data, n, out.ctypes.data, device))
+    return out
