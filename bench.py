@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the dual-annealing hot path (BASELINE.json metric: objective evals/sec,
+Rastrigin D=50, 64K chains).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One STEP = one complete pass of the hot path over one batch: 65,536 independent `sda` runs of
+Rastrigin D=50 on [-5.12, 5.12]^50 with the reference's defaults (maxiter=1000, T0=5230,
+qv=2.62, qa=-5, local search on), one persistent launch.  `value` counts every objective
+evaluation the chains made (annealing + L-BFGS-B incl. the 2D per gradient, i.e. the reference's
+`ncall`), summed over all ranks, divided by the device time of the step (max over ranks).
+
+N > 1 (torchrun): chains are sharded, every rank runs its own 65,536 chains with disjoint Philox
+keys (weak scaling) and the per-chain records (x*, f*, ncall) are gathered on rank 0 over NCCL
+inside the timed step -- the only collective of the path.
+
+--impl reference times the CPU oracle port of the reference algorithm (oracle/, plain C, all host
+cores) on a bounded sample of the same workload.  The reference itself is pure Python and cannot
+travel to the GPU box; its measured speed on the build host is recorded in BASELINE.md.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM = 50
+N_CHAINS = 65536
+MAXITER = 1000
+METRIC = "objective evals/sec (Rastrigin D=50, 64K chains)"
+UNIT = "evals/s"
+
+# nominal FP64-flop equivalents used to convert transcendentals
+FLOP = dict(cos=32, exp=28, log=36, sqrt=12, div=12, fmod=20)
+
+
+def algorithmic_flops(dim, chain_evals, ls_evals):
+    """Algorithmic FP64 work of the reference's formulas (DESIGN.md "Roofline arithmetic").
+    objective (Rastrigin, per eval): D x {cos, 2 mul, 1 fma(2), 1 add} ;
+    sampler (per visit sample): 2.546 uniforms -> X,Y,s (6), log, div, mul, sqrt, 2 mul, mul sigma,
+    log, mul, div, exp, div, clip/add (3), 2 fmod, 3 add ; (D^2 + D) samples per 2D evals."""
+    obj = dim * (FLOP["cos"] + 5)
+    sample = (6 + FLOP["log"] + FLOP["div"] + 1 + FLOP["sqrt"] + 3 + FLOP["log"] + 1 + FLOP["div"]
+              + FLOP["exp"] + FLOP["div"] + 3 + 2 * FLOP["fmod"] + 3)
+    sampler_per_eval = sample * (dim * dim + dim) / (2.0 * dim)
+    accept = FLOP["log"] + FLOP["exp"] + 2 * FLOP["div"] + 4
+    return chain_evals * (obj + sampler_per_eval + accept) + ls_evals * obj
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[4:8]) if v.startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference_run(n_chains, n_threads, maxiter, pure_sa):
+    """The oracle port of the reference algorithm on the host cores: (evals, seconds)."""
+    from oracle import sda_oracle as orc
+    orc.build()
+    P = orc.Problem("Rastrigin", [(-5.12, 5.12)] * DIM)
+    seeds = np.arange(n_chains, dtype=np.uint64) + np.uint64(7_000_000)
+    t0 = time.perf_counter()
+    o = orc.run(P, n_chains, seeds=seeds, maxiter=maxiter, pure_sa=pure_sa, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return int(o["ncall"].sum()), dt, o
+
+
+def config_dict(args, n_gpus):
+    return {"workload": "configs[2]-shaped batch at the metric's size: Rastrigin D=50, 65,536 "
+                        "chains/GPU, bounds [-5.12,5.12]^50, x0=None, sda defaults "
+                        "(maxiter=%d, T0=5230, qv=2.62, qa=-5), local search %s, Philox keys"
+                        % (args.maxiter, "off (pure_sa)" if args.pure_sa else "on (L-BFGS-B)"),
+            "chains_per_gpu": args.chains, "dim": DIM, "maxiter": args.maxiter,
+            "pure_sa": bool(args.pure_sa), "sharding": "chains x%d ranks, no data-path collective; "
+            "end-of-run NCCL gather of (x*, f*, ncall)" % n_gpus,
+            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_chains = max(cores, 8) * 2
+    vals, times = [], []
+    for it in range(args.warmup + args.steps):
+        evals, dt, _ = cpu_reference_run(n_chains, cores, args.maxiter, args.pure_sa)
+        if it >= args.warmup:
+            vals.append(evals)
+            times.append(dt)
+    value = float(sum(vals) / sum(times))
+    sample = "%d chains x maxiter=%d per step on %d threads (oracle/ C port, pthreads)" % (
+        n_chains, args.maxiter, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sdaopt_b200 import _lib, build as sda_build
+    from sdaopt_b200.device import DeviceBatch
+    import sdaopt_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(_lib.LIB_PATH):
+        sda_build.build()
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    f = sb.Rastrigin(DIM)
+    batch = DeviceBatch(f, f.bounds, args.chains, maxiter=args.maxiter, pure_sa=args.pure_sa,
+                        device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rec = torch.empty((args.chains, DIM + 3), dtype=torch.float64, device=dev)
+    gathered = ([torch.empty_like(rec) for _ in range(world)] if (world > 1 and rank == 0) else None)
+    step_no = [0]
+
+    def set_keys(host):
+        # fresh, disjoint Philox keys per (step, rank): no step repeats an earlier one's work
+        base = (step_no[0] * world + rank) * args.chains + 1_000_003
+        step_no[0] += 1
+        keys = torch.arange(base, base + args.chains, dtype=torch.int64)
+        if host:
+            batch.h_seeds.copy_(keys)
+        else:
+            batch.seeds.copy_(keys.to(dev))
+
+    def gather_records():
+        if world == 1:
+            return
+        rec[:, :DIM] = batch.out["x"]
+        rec[:, DIM] = batch.out["fun"]
+        rec[:, DIM + 1] = batch.out["ncall"].to(torch.float64)
+        rec[:, DIM + 2] = batch.out["nit"].to(torch.float64)
+        dist.gather(rec, gathered, dst=0)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn):
+        flush.fill_(step_no[0] & 0xff)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident_step():
+        batch.launch()
+        gather_records()
+
+    def host_step():
+        batch.run_from_host()
+        gather_records()
+
+    def totals():
+        t = torch.stack([batch.out["ncall"].sum(), batch.out["ncall_ls"].sum(),
+                         batch.out["n_ls"].sum(), (batch.out["status"] != 0).sum()]).to(torch.float64)
+        if world > 1:
+            dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    # ---- `value`: inputs resident in HBM --------------------------------------------------
+    for _ in range(args.warmup):
+        set_keys(False)
+        timed(resident_step)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_steps, evals, ls_evals, n_ls, bad = [], 0.0, 0.0, 0.0, 0.0
+    kernel_ms = []
+    for _ in range(args.steps):
+        set_keys(False)
+        # the dominant kernel alone, CUDA events on its launching stream
+        ms_steps.append(timed(resident_step))
+        kernel_ms.append(ms_steps[-1])
+        t = totals()
+        evals += t[0]; ls_evals += t[1]; n_ls += t[2]; bad += t[3]
+    # ---- `e2e`: pinned host inputs -> device, run, records -> host, every step -------------
+    e2e_ms, e2e_evals = [], 0.0
+    for _ in range(args.steps):
+        set_keys(True)
+        e2e_ms.append(timed(host_step))
+        e2e_evals += totals()[0]
+    clocks = sampler.stop()
+
+    total_s = sum(ms_steps) * 1e-3
+    value = evals / total_s
+    e2e_value = e2e_evals / (sum(e2e_ms) * 1e-3)
+
+    if rank == 0:
+        # roofline of the dominant kernel (sda_anneal_kernel<philox>): FP64 pipe
+        import ctypes as C
+        peak, pms = C.c_double(), C.c_double()
+        _lib.check(_lib.lib().sda_fp64_peak(C.byref(peak), C.byref(pms), local_rank))
+        per_gpu_chain = (evals - ls_evals) / world / args.steps
+        per_gpu_ls = ls_evals / world / args.steps
+        flops = algorithmic_flops(DIM, per_gpu_chain, per_gpu_ls)
+        achieved = flops / (np.mean(kernel_ms) * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("sda_anneal_kernel")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "fp64", "kernel": "sda_anneal_kernel<philox>", "achieved": achieved,
+                    "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
+                    "traffic": traffic,
+                    "peak_source": "DFMA microbenchmark run in this process (sda_fp64_peak); "
+                                   "MEASURED_PEAKS.json holds no FP64 figure; nominal 148x64x2x1.965 GHz = 37.2",
+                    "algorithmic_flops_per_launch": flops,
+                    "hbm_note": "chain state lives in shared memory; compulsory HBM traffic is "
+                                "(2D+6)*8 B per chain per run plus the L-BFGS-B slots (L2 resident)"}
+        cpu = None
+        if world == 1 or True:
+            cores = os.cpu_count() or 1
+            n = max(cores, 8) * 2
+            ce, cdt, _ = cpu_reference_run(n, cores, args.maxiter, args.pure_sa)
+            cpu = {"value": ce / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d chains x maxiter=%d of the same workload, %.1f s, oracle/ C port on "
+                             "%d pthreads" % (n, args.maxiter, cdt, cores)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": float(np.mean(ms_steps)),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config_dict(args, world),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes() * world,
+                        "d2h_bytes_per_step": batch.d2h_bytes() * world,
+                        "ms_per_step": float(np.mean(e2e_ms))},
+                "gpu_launches": 2 * args.steps * world,
+                "roofline": roofline, "cpu_baseline": cpu,
+                "breakdown": {"evals_per_step": evals / args.steps,
+                              "chain_steps_per_s": (evals - ls_evals) / total_s,
+                              "ls_evals_fraction": ls_evals / max(evals, 1.0),
+                              "local_searches_per_step": n_ls / args.steps,
+                              "chains_with_error": bad}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=N_CHAINS)
+    ap.add_argument("--maxiter", type=int, default=MAXITER)
+    ap.add_argument("--pure-sa", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -32,13 +32,18 @@ constexpr double kGradEps = 1.e-6;   // self.reps                               
 __host__ __device__ inline long long ls_workspace_doubles(int n)
 {
     const int m = kLsM;
-    // ws, wy | sy ss wt | wn snd | z r d t xp g x | wa | 3 int arrays (as 2n doubles)
-    return 2LL * m * n + 3LL * m * m + 8LL * m * m + 7LL * n + 8LL * m + 2LL * n + 8;
+    // ws, wy | sy ss wt | wn snd | z r d t xp g x xl gl | wa | 3 int arrays (as 2n doubles)
+    return 2LL * m * n + 3LL * m * m + 8LL * m * m + 9LL * n + 8LL * m + 2LL * n + 8;
 }
 
 struct LsWork {
     int n;
     double *ws, *wy, *sy, *ss, *wt, *wn, *snd, *z, *r, *d, *t, *xp, *g, *x, *wa;
+    // SciPy's ScalarFunction keeps the last evaluated point: a request at a bit-identical x is
+    // served from (xl, fl, gl) without calling the objective (no ncall, no monitor tick)
+    double *xl, *gl;
+    double fl;
+    int cache_valid;
     int *index, *iwhere, *indx2;
     __device__ void bind(double *base, int n_)
     {
@@ -49,7 +54,8 @@ struct LsWork {
         sy = q; q += m * m;  ss = q; q += m * m;  wt = q; q += m * m;
         wn = q; q += 4 * m * m;  snd = q; q += 4 * m * m;
         z = q; q += n;  r = q; q += n;  d = q; q += n;  t = q; q += n;  xp = q; q += n;
-        g = q; q += n;  x = q; q += n;
+        g = q; q += n;  x = q; q += n;  xl = q; q += n;  gl = q; q += n;
+        cache_valid = 0;
         wa = q; q += 8 * m;
         index = reinterpret_cast<int *>(q);
         iwhere = index + n;
@@ -748,11 +754,22 @@ __device__ inline int ls_dcsrch(LsSearch &s, int start, double f, double g, doub
 // ---- K7: f and the clipped central-difference gradient at x                        :325-345 ----
 // xe is the warp's shared-memory evaluation buffer.  Returns true when the suite monitor stopped
 // the chain (the reference would have raised out of scipy at that call).
-__device__ inline bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st, const double *x,
-                                       double *xe, const double *lo, const double *up, double &f,
-                                       double *g, int lane)
+__device__ inline bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st, LsWork &w,
+                                       const double *x, double *xe, const double *lo,
+                                       const double *up, double &f, double *g, int lane)
 {
     const int n = a.dim;
+    if (w.cache_valid) {
+        int same = 1;
+        for (int k = lane; k < n; k += SDA_WARP)
+            same &= (__double_as_longlong(x[k]) == __double_as_longlong(w.xl[k]));
+        if (__all_sync(SDA_FULL_MASK, same)) {
+            for (int k = lane; k < n; k += SDA_WARP) g[k] = w.gl[k];
+            f = w.fl;
+            __syncwarp();
+            return false;
+        }
+    }
     for (int k = lane; k < n; k += SDA_WARP) xe[k] = x[k];
     __syncwarp();
     f = func_wrapper(a, st, xe, lane, true);
@@ -777,8 +794,11 @@ __device__ inline bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st, cons
         if (lane == 0) xe[i] = xi;
         double gi = (f1 - f2) / (respl + respr);
         if (isnan(gi) || isinf(gi)) gi = 101.0;
-        if (lane == 0) g[i] = gi;
+        if (lane == 0) { g[i] = gi; w.gl[i] = gi; }
     }
+    for (int k = lane; k < n; k += SDA_WARP) w.xl[k] = x[k];
+    w.fl = f;
+    w.cache_valid = 1;
     __syncwarp();
     return false;
 }
@@ -807,7 +827,7 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
     int iter = 0, nenter = 0, ileave = 0, info = 0, wrk = 0;
     double theta = 1.0, fold = 0.0, sbgnrm, stp = 0.0, gd = 0.0, gdold = 0.0, dtd = 0.0, stpmx = 0.0;
 
-    if (ls_fun_and_grad(a, st, x, xe, l, u, f, g, lane)) { f_out = f; return -1; }
+    if (ls_fun_and_grad(a, st, w, x, xe, l, u, f, g, lane)) { f_out = f; return -1; }
     nfev = 1;
     sbgnrm = ls_projgr(n, l, u, x, g, lane);
     if (sbgnrm <= kLsPgtol) { f_out = f; return 0; }
@@ -910,7 +930,7 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
                     break;
                 }
                 if (lstask == kLsFG) {
-                    if (ls_fun_and_grad(a, st, x, xe, l, u, f, g, lane)) { f_out = f; return -1; }
+                    if (ls_fun_and_grad(a, st, w, x, xe, l, u, f, g, lane)) { f_out = f; return -1; }
                     continue;
                 }
                 break;
@@ -970,6 +990,7 @@ __device__ __noinline__ int ofw_local_search(const DeviceArgs &a, ChainState &st
     for (int k = lane; k < a.dim; k += SDA_WARP) w.x[k] = x_start[k];
     __syncwarp();
     st.n_ls += 1;
+    w.cache_valid = 0;
     const int warnflag = lbfgsb_minimize(a, st, w, xe, lo, up, e, a.ls_maxiter, lane);
     __syncwarp();
     if (warnflag != 0) { e = kBigValue; return 0; }

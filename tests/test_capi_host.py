@@ -1,0 +1,136 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sdaopt_b200.h declares, fails
+loudly without a GPU (no CPU fallback), and the host-side mirror of the reference interface
+validates arguments like the reference.  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, has_cuda
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "sdaopt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sdaopt_b200 import _lib
+    L = _lib.lib()
+    names = _declared_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), "libsdaopt_b200.so does not export %s" % n
+    assert sorted(_lib.EXPORTS) == names
+    assert L.sda_abi_version() == 1
+
+
+def test_functor_table_matches_oracle_ids(oracle):
+    from sdaopt_b200 import _lib, functors
+    L = _lib.lib()
+    for name, fid in functors.FUNCTOR_IDS.items():
+        assert L.sda_functor_id(name.encode()) == fid
+        assert L.sda_functor_name(fid).decode() == name
+        assert oracle.FN[name] == fid
+    assert L.sda_functor_id(b"NoSuchFunction") == _lib.SDA_E_INVALID
+
+
+def test_struct_layouts_match_header():
+    from sdaopt_b200 import _lib
+    # SdaProblem: 2 x int32, 3 pointers, int32 (+pad); SdaConfig: see include/sdaopt_b200.h
+    assert C.sizeof(_lib.SdaProblem) == 40
+    assert C.sizeof(_lib.SdaConfig) == 8 * 15
+    assert C.sizeof(_lib.SdaResult) == 8 * 13
+    assert [n for n, _ in _lib.SdaResult._fields_] == list(_lib.RESULT_FIELDS)
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import sdaopt_b200
+    from sdaopt_b200 import _lib
+    with pytest.raises(_lib.SdaError):
+        sdaopt_b200.sda(sdaopt_b200.Rastrigin(), None, [(-5.12, 5.12)] * 2)
+    with pytest.raises(_lib.SdaError):
+        sdaopt_b200.Rastrigin()(np.zeros(2))
+    with pytest.raises(_lib.SdaError):
+        sdaopt_b200.sda_batch("Rastrigin", [(-5.12, 5.12)] * 2, 4)
+
+
+def test_argument_validation_mirrors_reference():
+    import sdaopt_b200 as sb
+    # _sda.py:360-361, :366-367 raise before any device work
+    with pytest.raises(ValueError, match="Bounds size does not match x0"):
+        sb.SDARunner(sb.Rastrigin(), np.zeros(3), [(-5.12, 5.12)] * 2)
+    with pytest.raises(ValueError, match="Bounds are note consistent"):
+        sb.SDARunner(sb.Rastrigin(), None, [(-5.12, 5.12), (1, 0), (5.12, 5.12)])
+    with pytest.raises(ValueError, match="Bounds are note consistent"):
+        sb.SDARunner(sb.Rastrigin(), None, [(5.12, 5.12)] * 2)
+    with pytest.raises(TypeError):
+        sb.SDARunner(lambda x: float(np.sum(x * x)), None, [(-1, 1)] * 2)
+    with pytest.raises(NotImplementedError):
+        sb.SDARunner(sb.Rastrigin(), None, [(-1, 1)] * 2, minimizer_kwargs={"method": "BFGS"})
+    owf = sb.ObjectiveFunWrapper([(-1, 1)] * 30, "Rastrigin")
+    assert owf.ls_max_iter == 180 and owf.nb_fun_call == 0          # :291-296
+    assert sb.ObjectiveFunWrapper([(-1, 1)] * 2, "Sphere").ls_max_iter == 100
+    assert sb.ObjectiveFunWrapper([(-1, 1)] * 500, "Sphere").ls_max_iter == 1000
+
+
+def test_functor_resolution():
+    import sdaopt_b200 as sb
+    from sdaopt_b200 import functors
+
+    class Rastrigin(object):          # stands for go_benchmark_functions.Rastrigin
+        N = 7
+
+        def fun(self, x, *args):
+            return 0.0
+
+    class Algo(object):               # benchmark/bench.py:292: bound _funcwrapped with self._k
+        def __init__(self):
+            self._k = Rastrigin()
+
+        def _funcwrapped(self, x):
+            return 0.0
+
+    def sutton_chen(x):
+        return 0.0
+
+    assert functors.resolve(Rastrigin().fun).name == "Rastrigin"
+    assert functors.resolve(Algo()._funcwrapped).N == 7
+    assert functors.resolve(sutton_chen).name == "SuttonChen"
+    assert functors.resolve("Ackley01").functor_id == 3
+    assert functors.resolve(sb.ShiftedRastrigin(3.14159)).params[0] == 3.14159
+    assert sb.Rastrigin(10).bounds == [(-5.12, 5.12)] * 10 and sb.Exponential(3).fglob == -1.0
+
+
+def test_k1_tables_are_the_reference_formulas():
+    """temperature_tables() is host logic: bit-identical to the tables the reference computed."""
+    from sdaopt_b200._sda import temperature_tables, sigmax
+    g = load_golden("sampler.npz")
+    T, S = temperature_tables(1400)
+    # the golden tables were computed under numpy's libm dispatch; this host may use AVX-512
+    # loops (1-ulp exp/log differences), so compare to 4 ulp
+    np.testing.assert_allclose(T, g["temp_table"], rtol=1e-15)
+    np.testing.assert_allclose(S, g["sigmax_table"], rtol=2e-14)
+    assert len(T) == 1282 and T[-1] < 0.1 <= T[-2]
+    assert sigmax(5230., 2.62) == pytest.approx(31475975860.533634, rel=1e-13)
+    T2, _ = temperature_tables(50)
+    assert len(T2) == 50
+
+
+def test_workspace_size_is_monotone():
+    from sdaopt_b200 import _lib, functors
+    L = _lib.lib()
+    f = functors.DeviceFunctor("Rastrigin")
+    lo = np.zeros(50)
+    p, keep = functors.make_problem(f, lo, lo + 1)
+    cfg = _lib.SdaConfig(1000, 5230., 2.62, -5.0, 1e7, 0, 0.1, 0, 0, float("nan"), 1e-8, 0, None, None, 0)
+    a = L.sda_workspace_bytes(C.byref(p), C.byref(cfg), 1024)
+    b = L.sda_workspace_bytes(C.byref(p), C.byref(cfg), 65536)
+    cfg.pure_sa = 1
+    c = L.sda_workspace_bytes(C.byref(p), C.byref(cfg), 65536)
+    assert 0 < a < b and c < b
+    assert L.sda_workspace_bytes(None, C.byref(cfg), 4) == 0

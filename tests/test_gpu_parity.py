@@ -1,0 +1,327 @@
+"""GPU: the CUDA path, called through the C ABI (libsdaopt_b200.so), against the CPU oracle and
+the golden fixtures recorded from the live reference.
+
+Tolerances (DESIGN.md "Parity"): decisions and draw counts are compared exactly; objective values
+at identical points to 1e-12 relative (floor 1e-12 * 10 D for the cancelling `10 D + sum` forms);
+trajectory energies to 2e-6 relative -- a proposal x + visit with |visit| up to 1e8 carries the
+1-ulp difference between CUDA's, glibc's and numpy's exp/log as an absolute error up to ~1e-8 in
+x, and the reference itself moves by that much between numpy builds (tests/golden/asrun_*)."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, load_golden, tape_from_seed
+
+pytestmark = pytest.mark.gpu
+
+TRAJ = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "traj_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import sdaopt_b200
+    from sdaopt_b200 import _lib
+    assert _lib.lib().sda_device_count() > 0, "CUDA device required: no CPU fallback"
+    return sdaopt_b200
+
+
+def _functor(sb, name, params):
+    return sb.DeviceFunctor(name, params=params if params is not None and len(params) else ())
+
+
+def _energy_close(e, ref, dim, rel):
+    floor = 1e-12 * 10.0 * dim
+    return np.abs(e - ref) <= np.maximum(rel * np.abs(ref), floor)
+
+
+# ---- K3: objectives -----------------------------------------------------------------------------
+def test_objectives_match_reference_and_oracle(sb, oracle):
+    rows = load_golden("objective_points.npz")["rows"]
+    for r in rows:
+        f = _functor(sb, r["functor"], r["params"])
+        F = f(r["X"])
+        tol = 1e-12 if r["functor"] != "SuttonChen" else 1e-11
+        ok = _energy_close(F, r["F"], r["dim"], tol)
+        assert ok.all(), (r["functor"], r["dim"], F[~ok], r["F"][~ok])
+        P = oracle.Problem(r["functor"], r["bounds"], params=r["params"] if len(r["params"]) else None)
+        Fo = np.array([P.eval(x) for x in r["X"]])
+        assert _energy_close(F, Fo, r["dim"], tol).all()
+
+
+def test_sutton_chen_known_answer_and_sizes(sb, oracle):
+    xg = load_golden("objective_points.npz")["rows"][-3]["X"][0]
+    assert sb.SuttonChen(6)(xg) == pytest.approx(-1163.9639632, abs=5e-8)      # suttonchen.py:43-52
+    for n_atoms in (38, 128, 512):
+        X = np.random.RandomState(n_atoms).uniform(-2, 2, (3, 3 * n_atoms)) * (n_atoms / 6) ** (1 / 3)
+        F = sb.SuttonChen(n_atoms)(X)
+        P = oracle.Problem("SuttonChen", [(-20, 20)] * (3 * n_atoms))
+        Fo = np.array([P.eval(x) for x in X])
+        np.testing.assert_allclose(F, Fo, rtol=1e-11)
+
+
+# ---- K2: visiting distribution --------------------------------------------------------------------
+def test_visit_fn_against_reference(sb):
+    from sdaopt_b200 import _lib
+    g = load_golden("sampler.npz")
+    tape = tape_from_seed(1234, 40000)
+    for T in (5230., 100., 0.1):
+        vals = g["visit_fn_T%g" % T]
+        a, b = g["visit_fn_T%g_tape" % T]
+        i = {5230.: 0}.get(T)
+        sig = float(g["sigmax_table"][0]) if T == 5230. else sb._sda.sigmax(T, 2.62)
+        out = np.empty(len(vals))
+        used = C.c_int64()
+        t = np.ascontiguousarray(tape[a:b])
+        _lib.check(_lib.lib().sda_visit_fn_host(2.62, sig, t.ctypes.data, t.size, out.ctypes.data,
+                                                 len(vals), C.byref(used), 0))
+        assert used.value == b - a                      # identical polar rejections
+        np.testing.assert_allclose(out, vals, rtol=5e-13)
+
+
+def test_visiting_stepping_reference_unit_tests(sb):
+    """test_sda.py:51-64 and SURVEY App. C.1 anchors, through the mirrored class."""
+    from scipy._lib._util import check_random_state
+    g = load_golden("sampler.npz")
+    lower, upper = np.array([-5.12] * 2), np.array([5.12] * 2)
+    rs = check_random_state(1234)
+    vd = sb.VisitingDistribution(lower, upper, 2.62, rs)
+    x_step_low = vd.visiting(np.zeros(2), 0, 5230)
+    assert np.all(x_step_low != 0)
+    np.testing.assert_allclose(x_step_low, g["visiting_step0"], rtol=1e-13)
+    x_step_high = vd.visiting(np.zeros(2), 2, 5230)
+    assert x_step_high[0] != 0 and x_step_high[1] == 0
+    np.testing.assert_allclose(x_step_high, g["visiting_step2"], rtol=1e-13)
+    # the RandomState advanced by exactly what the reference consumed
+    ref_rs = np.random.RandomState(1234)
+    ref_rs.random_sample(int(g["visiting_step2_tape"]))
+    assert rs.random_sample() == ref_rs.random_sample()
+
+
+def test_visiting_dist_high_temperature_and_gaussian(sb):
+    """test_sda.py:66-79 and :93-103 (statistical), via the device sampler on a tape."""
+    from sdaopt_b200 import _lib
+    tape = tape_from_seed(1234, 20000)
+    out = np.empty(5000)
+    used = C.c_int64()
+    sig = sb._sda.sigmax(5230., 2.62)
+    _lib.check(_lib.lib().sda_visit_fn_host(2.62, sig, tape.ctypes.data, tape.size, out.ctypes.data,
+                                             5000, C.byref(used), 0))
+    assert out.min() < 1e-10 and out.max() > 1e10
+    # gaussian_fn(1) == visit kernel with qv = 1, sigmax = 1
+    _lib.check(_lib.lib().sda_visit_fn_host(1.0, 1.0, tape.ctypes.data, tape.size, out.ctypes.data,
+                                             5000, C.byref(used), 0))
+    assert abs(out.mean()) < 0.05 and abs(np.median(out)) < 0.05 and abs(out.std() - 1) < 0.05
+    from scipy._lib._util import check_random_state
+    vd = sb.VisitingDistribution(np.array([-5.12] * 2), np.array([5.12] * 2), 2.62,
+                                 check_random_state(1234))
+    v = np.array([vd.gaussian_fn(1) for _ in range(50)])
+    np.testing.assert_allclose(v, out[:50], rtol=1e-15)
+
+
+# ---- trajectory replay: the reference's RandomState draws injected ---------------------------------
+@pytest.mark.parametrize("fname", TRAJ)
+def test_trajectory_replay_against_reference(sb, oracle, fname):
+    g = load_golden(fname)
+    params = g["params"] if len(g["params"]) else None
+    f = _functor(sb, str(g["functor"]), params)
+    n_evals = len(g["energies"])
+    tape = tape_from_seed(int(g["seed"]), int(g["tape_len"]) + 4096)
+    x0 = g["x0"] if "x0" in g.files else None
+    r = sb.sda_batch(f, g["bounds"], 1, x0=x0, tape=tape, maxiter=int(g["maxiter"]), pure_sa=True,
+                     trace_len=n_evals)
+    assert r.status[0] == 0 and r.nit[0] == int(g["nit"]) and r.ncall[0] == int(g["ncall"])
+    dec, e = r.trace_d[0], r.trace_e[0]
+    same = dec == g["decisions"]
+    first_diff = int(np.argmin(same)) if not same.all() else n_evals
+    # rounding noise may flip a near-tie late in a long chain; everything before is identical
+    prefix = min(n_evals, 4000)
+    assert first_diff >= prefix, "decision %d differs" % first_diff
+    assert _energy_close(e[:first_diff], g["energies"][:first_diff], len(g["bounds"]), 2e-6).all()
+    if first_diff == n_evals:
+        assert r.tape_used[0] == int(g["tape_len"])
+        np.testing.assert_allclose(r.x[0], g["x"], rtol=0, atol=5e-6)
+        assert r.fun[0] == pytest.approx(float(g["fun"]), rel=2e-4, abs=1e-9)
+    # ... and against the C oracle on the same tape
+    P = oracle.Problem(str(g["functor"]), g["bounds"], params=params)
+    o = oracle.run(P, 1, x0=x0, tape=tape, maxiter=int(g["maxiter"]), pure_sa=True,
+                   trace_len=n_evals, tables=(g["temp_table"], g["sigmax_table"]))
+    assert (o["trace_d"][0][:first_diff] == dec[:first_diff]).all()
+
+
+# ---- production RNG: the oracle implements the same Philox addressing -------------------------------
+@pytest.mark.parametrize("name,dim,maxiter", [("Rastrigin", 50, 30), ("Ackley01", 10, 80),
+                                              ("Schwefel26", 10, 80), ("Rosenbrock", 2, 150),
+                                              ("Griewank", 7, 80), ("Rastrigin", 100, 8),
+                                              ("Exponential", 33, 40)])
+def test_philox_chains_match_oracle(sb, oracle, name, dim, maxiter):
+    f = sb.DeviceFunctor(name, dimensions=dim)
+    bounds = f.bounds
+    n = 24
+    seeds = np.arange(1000, 1000 + n, dtype=np.uint64) * np.uint64(2654435761)
+    n_evals = 2 * dim * (maxiter - 1)
+    r = sb.sda_batch(f, bounds, n, seeds=seeds, maxiter=maxiter, pure_sa=True, trace_len=n_evals)
+    tables = sb._sda.temperature_tables(maxiter)
+    o = oracle.run(oracle.Problem(name, bounds), n, seeds=seeds, maxiter=maxiter, pure_sa=True,
+                   trace_len=n_evals, tables=tables)
+    assert (r.ncall == o["ncall"]).all() and (r.nit == o["nit"]).all()
+    frac_same = np.mean(r.trace_d == o["trace_d"])
+    exact_chains = np.mean((r.trace_d == o["trace_d"]).all(axis=1))
+    assert exact_chains >= 0.9, (exact_chains, frac_same)
+    good = (r.trace_d == o["trace_d"]).all(axis=1)
+    assert _energy_close(r.trace_e[good], o["trace_e"][good], dim, 2e-6).all()
+    np.testing.assert_allclose(r.fun[good], o["fun"][good], rtol=1e-4, atol=1e-9)
+
+
+def test_reanneal_and_reinit(sb, oracle):
+    """maxiter beyond the restart index (T < 0.1 at i = 1281, _sda.py:408-410) and a start that
+    needs re-draws are handled like the oracle."""
+    f = sb.Rastrigin(2)
+    seeds = np.arange(8, dtype=np.uint64) + np.uint64(99)
+    r = sb.sda_batch(f, f.bounds, 8, seeds=seeds, maxiter=1400, pure_sa=True)
+    o = oracle.run(oracle.Problem("Rastrigin", f.bounds), 8, seeds=seeds, maxiter=1400,
+                   pure_sa=True, tables=sb._sda.temperature_tables(1400))
+    assert (r.nit == 1400).all() and (r.ncall == o["ncall"]).all()
+    assert (r.ncall == 4 * (1400 - 2)).all()          # one step is spent on the re-anneal
+    np.testing.assert_allclose(r.fun, o["fun"], rtol=1e-3, atol=1e-9)
+
+
+# ---- K6/K7: local search ------------------------------------------------------------------------------
+def test_local_search_against_scipy_and_oracle(sb, oracle):
+    rows = load_golden("lbfgsb_scipy.npz")["rows"]
+    same_nfev = 0
+    for r in rows:
+        owf = sb.ObjectiveFunWrapper(r["bounds"], r["functor"])
+        e, x = owf.local_search(r["x0"])
+        assert (x is not None) == bool(r["success"]), (r["functor"], r["dim"])
+        ok, xo, fo, nfev = oracle.local_search(oracle.Problem(r["functor"], r["bounds"]), r["x0"])
+        same_nfev += int(owf.nb_fun_call == nfev)
+        if x is None:
+            continue
+        if r["functor"] in ("Rastrigin", "Sphere", "Exponential", "Schwefel01", "Schwefel26", "Ackley01"):
+            assert e == pytest.approx(float(r["f"]), rel=1e-6, abs=1e-8), (r["functor"], r["dim"])
+            np.testing.assert_allclose(x, r["x"], atol=2e-5 * (1 + np.abs(r["x"]).max()))
+    assert same_nfev >= 0.7 * len(rows), same_nfev
+
+
+def test_local_search_zero_plateau_trap(sb):
+    """f rounds to 0 while |g| > gtol: SciPy's line search keeps shrinking the step until the
+    trial point stops changing, ScalarFunction then serves the cache, and the run ends ABNORMAL
+    after 28 requests = 476 calls (measured with scipy 1.18.1; oracle/lbfgsb_oracle.h)."""
+    owf = sb.ObjectiveFunWrapper([(-5.12, 5.12)] * 8, "Rastrigin")
+    e, x = owf.local_search(np.array([6e-9, 0, 0, 0, 0, 0, 0, 0.]))
+    assert x is None and e == 1e16 and owf.nb_fun_call == 476
+
+
+# ---- whole runs: the reference's own tests (sdaopt/tests/test_sda.py) ----------------------------------
+def test_low_dim(sb):
+    ret = sb.sda(sb.Rastrigin(), None, [(-5.12, 5.12)] * 2, seed=1234)
+    np.testing.assert_allclose(ret.fun, 0., atol=1e-12)
+    assert set(ret.keys()) == {"x", "fun", "nit", "ncall"} and ret.nit == 1000
+
+
+def test_high_dim(sb):
+    ret = sb.sda(sb.Rastrigin(), None, [(-5.12, 5.12)] * 8)
+    np.testing.assert_allclose(ret.fun, 0., atol=1e-12)
+
+
+def test_reproduce(sb):
+    res = [sb.sda(sb.Rastrigin(), None, [(-5.12, 5.12)] * 2, seed=1234) for _ in range(3)]
+    np.testing.assert_equal(res[0].x, res[1].x)
+    np.testing.assert_equal(res[0].x, res[2].x)
+
+
+def test_max_reinit_and_reset(sb):
+    with pytest.raises(ValueError):
+        sb.sda(sb.Constant(2e16), None, [(-5.12, 5.12)] * 2)
+    from scipy._lib._util import check_random_state
+    owf = sb.ObjectiveFunWrapper([(-5.12, 5.12)] * 2, sb.Constant(2e16))
+    es = sb.EnergyState(np.array([-5.12] * 2), np.array([5.12] * 2))
+    with pytest.raises(ValueError):
+        es.reset(owf, check_random_state(None))
+
+
+def test_bounds_integrity(sb):
+    with pytest.raises(ValueError):
+        sb.sda(sb.Rastrigin(), None, [(-5.12, 5.12), (1, 0), (5.12, 5.12)])
+    with pytest.raises(ValueError):
+        sb.sda(sb.Rastrigin(), np.zeros(3), [(-5.12, 5.12)] * 2)
+    with pytest.raises(TypeError):
+        sb.sda(lambda x: 0.0, None, [(-5.12, 5.12)] * 2)
+
+
+def test_tape_mode_replays_reference_run_with_local_search(sb):
+    """rng='tape': the RandomState uniforms themselves drive the run (SURVEY App. C.4 anchors)."""
+    rows = load_golden("ls_runs.npz")["rows"]
+    exact = 0
+    for r in rows[:5]:
+        f = sb.DeviceFunctor(r["functor"], dimensions=r["dim"])
+        ret = sb.sda(f, None, r["bounds"], seed=int(r["seed"]), rng="tape")
+        assert ret.nit == 1000
+        assert ret.fun == pytest.approx(r["fun"], abs=1e-8)
+        assert abs(ret.ncall - r["ncall"]) <= 0.10 * r["ncall"]
+        exact += int(ret.ncall == r["ncall"])
+    assert exact >= 2, exact
+
+
+def test_readme_examples(sb):
+    """README.md:28-39 and :41-80 (BASELINE configs 1 and 2 with local search)."""
+    ret = sb.sda(sb.Rosenbrock(), None, [(-30, 30)] * 2, seed=1234)
+    assert ret.fun < 1e-8 and np.allclose(ret.x, 1.0, atol=1e-3) and ret.nit == 1000
+    np.random.seed(1234)
+    lower, upper = np.array([-5.12] * 50), np.array([10.24] * 50)
+    x_init = lower + np.random.rand(50) * (upper - lower)
+    ret = sb.sda(sb.ShiftedRastrigin(3.14159), x_init, list(zip(lower, upper)), seed=1234)
+    assert ret.fun < 1e-8 and np.allclose(ret.x, 3.14159, atol=1e-4)
+    assert 99900 < ret.ncall < 200000
+
+
+# ---- statistical parity with local search on (north star, second criterion) ---------------------------
+def _wilson(k, n, z=1.96):
+    p = k / n
+    d = 1 + z * z / n
+    c = p + z * z / (2 * n)
+    h = z * np.sqrt(p * (1 - p) / n + z * z / (4 * n * n))
+    return (c - h) / d, (c + h) / d
+
+
+@pytest.mark.parametrize("name,dim", [("Rastrigin", 2), ("Rastrigin", 10), ("Ackley01", 10),
+                                      ("Rosenbrock", 2), ("Schwefel01", 5)])
+def test_suite_statistics_match_oracle(sb, oracle, name, dim):
+    """Suite semantics (bench.py:292-321) over NB_RUNS=100 seeds: success rate inside the oracle's
+    Wilson 95 % interval and median ncall-to-global inside its order-statistic interval."""
+    f = sb.DeviceFunctor(name, dimensions=dim)
+    n = 100
+    seeds = np.arange(n, dtype=np.uint64) + np.uint64(1234)
+    kw = dict(maxiter=int(1e6), max_calls=100000, fglob=f.fglob, tol=1e-8)
+    r = sb.sda_batch(f, f.bounds, n, seeds=seeds, **kw)
+    o = oracle.run(oracle.Problem(name, f.bounds), n, seeds=seeds, n_threads=8,
+                   tables=sb._sda.temperature_tables(int(1e6)), **kw)
+    lo, hi = _wilson(int(o["hit"].sum()), n)
+    assert lo - 1e-9 <= r.hit.mean() <= hi + 1e-9 or r.hit.sum() == o["hit"].sum()
+    so = np.sort(o["ncall_hit"])
+    # distribution-free 95 % CI of the median for n = 100: order statistics 40 and 61
+    assert so[39] <= np.median(r.ncall_hit) <= so[60], (np.median(r.ncall_hit), so[39], so[60])
+    # the same seeds give the same first hits unless L-BFGS-B noise moved a chain
+    assert np.mean(r.ncall_hit == o["ncall_hit"]) > 0.5
+
+
+# ---- full-size properties (BASELINE config 3 shape) ------------------------------------------------------
+def test_full_size_batch_properties(sb):
+    """65,536 Rastrigin D=50 chains (short schedule): every chain reports nit == maxiter, exactly
+    2 D (maxiter - 1) annealing calls, a best point inside the box whose energy is reproduced by
+    an independent evaluation, and two launches with the same seeds are bit-identical."""
+    f = sb.Rastrigin(50)
+    n, maxiter = 65536, 6
+    r1 = sb.sda_batch(f, f.bounds, n, maxiter=maxiter, pure_sa=True)
+    r2 = sb.sda_batch(f, f.bounds, n, maxiter=maxiter, pure_sa=True)
+    assert (r1.status == 0).all() and (r1.nit == maxiter).all()
+    assert (r1.ncall == 2 * 50 * (maxiter - 1)).all()
+    assert (r1.x >= -5.12).all() and (r1.x <= 5.12).all()
+    np.testing.assert_array_equal(r1.x, r2.x)
+    np.testing.assert_array_equal(r1.fun, r2.fun)
+    F = f(r1.x[::64])
+    np.testing.assert_allclose(F, r1.fun[::64], rtol=1e-13)
+    assert len(np.unique(r1.fun)) > 0.99 * n           # independent streams
