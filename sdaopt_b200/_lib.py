@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdaopt_b200.so")
+LIB_PATH = os.environ.get("SDA_LIB_PATH") or os.path.join(_HERE, "libsdaopt_b200.so")  # override: A/B builds
 
 SDA_OK = 0
 SDA_E_INVALID, SDA_E_BOUNDS, SDA_E_CUDA, SDA_E_WORKSPACE, SDA_E_UNSUPPORTED = -1, -2, -3, -4, -5

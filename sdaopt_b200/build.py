@@ -36,7 +36,8 @@ def build(force=False, verbose=False):
     """Compile the CUDA library if it is missing or older than its sources."""
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("SDA_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return LIB

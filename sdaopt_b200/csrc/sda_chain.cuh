@@ -41,6 +41,11 @@ struct DeviceArgs {
     int ls_maxiter;                 // clamp(6*dim, 100, 1000)  _sda.py:291-296
 };
 
+// the search box in shared memory: lower, upper, upper - lower and 1 / (upper - lower)
+struct Box {
+    const double *lo, *up, *range, *inv_range;
+};
+
 struct ChainState {
     double e_cur, ebest, emin;
     long long not_improved_idx, not_improved_max_idx;
@@ -208,8 +213,7 @@ template <bool TAPE>
 __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, Rng<TAPE> &rng,
                                            long long chain, long long step, double temperature,
                                            double sigmax, double *x_cur, double *x_vis, double *sv,
-                                           const double *lo, const double *up, double *xbest,
-                                           double *xmin, int lane)
+                                           const Box &bx, double *xbest, double *xmin, int lane)
 {
     const int dim = a.dim;
     const double t_step = __ddiv_rn(temperature, (double)(step + 1));
@@ -233,17 +237,29 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                     double v = sv[k];
                     if (v > kTailLimit) v = __dmul_rn(kTailLimit, upper_sample);
                     else if (v < -kTailLimit) v = __dmul_rn(-kTailLimit, lower_sample);
-                    x_vis[k] = wrap_coord(__dadd_rn(v, x_cur[k]), lo[k], __dsub_rn(up[k], lo[k]));
+                    x_vis[k] = wrap_coord(__dadd_rn(v, x_cur[k]), bx.lo[k], bx.range[k], bx.inv_range[k]);
                 }
             } else {
                 rng.p.j = (uint32_t)j;
                 double upper_sample, lower_sample;
                 rng.p.pair(kClip, 0, 0, upper_sample, lower_sample);
-                for (int k = lane; k < dim; k += SDA_WARP) {
-                    double v = visit_sample_philox(rng.p, (uint32_t)k, vc);
-                    if (v > kTailLimit) v = __dmul_rn(kTailLimit, upper_sample);
-                    else if (v < -kTailLimit) v = __dmul_rn(-kTailLimit, lower_sample);
-                    x_vis[k] = wrap_coord(__dadd_rn(v, x_cur[k]), lo[k], __dsub_rn(up[k], lo[k]));
+                // two coordinates per lane and trip: the two log/sqrt/exp/div chains are
+                // independent, which doubles the ILP of the FP64 pipe at 4 warps per SMSP
+                for (int k0 = lane; k0 < dim; k0 += 2 * SDA_WARP) {
+                    const int k1 = k0 + SDA_WARP;
+                    const bool two = k1 < dim;
+                    double xg0, yg0, s0, xg1 = 0.5, yg1 = 0.5, s1 = 0.5;
+                    polar_pair_philox(rng.p, (uint32_t)k0, xg0, yg0, s0);
+                    if (two) polar_pair_philox(rng.p, (uint32_t)k1, xg1, yg1, s1);
+                    double v0 = visit_from_polar(xg0, yg0, s0, vc);
+                    double v1 = visit_from_polar(xg1, yg1, s1, vc);
+                    if (v0 > kTailLimit) v0 = __dmul_rn(kTailLimit, upper_sample);
+                    else if (v0 < -kTailLimit) v0 = __dmul_rn(-kTailLimit, lower_sample);
+                    if (v1 > kTailLimit) v1 = __dmul_rn(kTailLimit, upper_sample);
+                    else if (v1 < -kTailLimit) v1 = __dmul_rn(-kTailLimit, lower_sample);
+                    x_vis[k0] = wrap_coord(__dadd_rn(v0, x_cur[k0]), bx.lo[k0], bx.range[k0], bx.inv_range[k0]);
+                    if (two)
+                        x_vis[k1] = wrap_coord(__dadd_rn(v1, x_cur[k1]), bx.lo[k1], bx.range[k1], bx.inv_range[k1]);
                 }
             }
             __syncwarp();
@@ -277,8 +293,8 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                 visit = sv[index];
             }
             if (lane == 0)
-                x_vis[index] = wrap_coord(__dadd_rn(visit, x_cur[index]), lo[index],
-                                          __dsub_rn(up[index], lo[index]));
+                x_vis[index] = wrap_coord(__dadd_rn(visit, x_cur[index]), bx.lo[index],
+                                          bx.range[index], bx.inv_range[index]);
             __syncwarp();
             single = index;
         }

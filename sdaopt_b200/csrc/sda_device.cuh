@@ -55,8 +55,12 @@ struct Philox {
 // numpy RandomState.random_sample() construction (genrand_res53)
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b)
 {
-    // (a>>5)*2^26 + (b>>6) < 2^53 is exact in double; the division by 2^53 is a power-of-two scale
-    return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * 1.1102230246251565e-16;
+    // ((a>>5)*2^26 + (b>>6)) / 2^53, exactly, without a 64-bit int->double conversion (XU pipe):
+    // 0x43300000:w is the double 2^52 + w, so subtracting 2^52 yields w exactly (FP64 pipe), and
+    // hi*2^-27 + lo*2^-53 has at most 53 significant bits, so the fma is exact too.
+    const double hi = __hiloint2double(0x43300000, (int)(a >> 5)) - 4503599627370496.0;
+    const double lo = __hiloint2double(0x43300000, (int)(b >> 6)) - 4503599627370496.0;
+    return fma(hi, 7.450580596923828125e-09, lo * 1.1102230246251565404e-16);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -113,12 +117,35 @@ __device__ __forceinline__ double visit_from_polar(double xg, double yg, double 
     return __ddiv_rn(x, den);                                          // :91
 }
 
+// C fmod(a, R) for R > 0, bit-exact, in ~8 FP64 instructions instead of libdevice's long-division
+// loop.  q = rint(|a|/R) (magic-number rounding), t = fma(-q, R, |a|) is the exact remainder as
+// long as q < 2^50: q carries a relative error <= 2^-52, so |t| < R and t is a multiple of
+// ulp(R) -> representable, the fma does not round.  fmod takes the sign of a.
+__device__ __forceinline__ double fmod_exact(double a, double R, double invR)
+{
+    const double aa = fabs(a);
+    if (aa < R) return a;
+    const double q = aa * invR;
+    if (!(q < 1125899906842624.0)) return fmod(a, R);      // 2^50: fall back (also inf/nan)
+    const double qi = __dadd_rn(__dadd_rn(q, 6755399441055744.0), -6755399441055744.0);
+    double t = __fma_rn(-qi, R, aa);
+    if (t < 0.0) t = __dadd_rn(t, R);
+    else if (t >= R) t = __dsub_rn(t, R);
+    return copysign(t, a);
+}
+
 // a = x - lower; b = fmod(a, R) + R; x = fmod(b, R) + lower; nudge      :50-55 / :65-72
-__device__ __forceinline__ double wrap_coord(double xv, double lower, double range)
+// invR = 1/R.  Every rounding of the reference's sequence is kept: fmod is exact by definition,
+// b = fmod(a,R) + R rounds once, and b lies in (0, 2R] so the second fmod is a conditional subtract.
+__device__ __forceinline__ double wrap_coord(double xv, double lower, double range, double inv_range)
 {
     const double a = __dsub_rn(xv, lower);
-    const double b = __dadd_rn(fmod(a, range), range);
-    double r = __dadd_rn(fmod(b, range), lower);
+    const double b = __dadd_rn(fmod_exact(a, range, inv_range), range);
+    double m = b;
+    if (m >= range) m = __dsub_rn(m, range);
+    if (m >= range) m = __dsub_rn(m, range);
+    if (!(b <= 2.0 * range && b >= 0.0)) m = fmod(b, range);   // not reachable for finite inputs
+    double r = __dadd_rn(m, lower);
     if (fabs(__dsub_rn(r, lower)) < kMinVisitBound) r = __dadd_rn(r, 1.e-10);
     return r;
 }
@@ -149,6 +176,20 @@ struct PhiloxRng {
         u2 = u53(o[2], o[3]);
     }
 };
+
+// accepted polar pair for coordinate k, Philox source                                :94-102
+__device__ __forceinline__ void polar_pair_philox(const PhiloxRng &rng, uint32_t k, double &xg,
+                                                  double &yg, double &s)
+{
+    uint32_t attempt = 0;
+    do {
+        double u1, u2;
+        rng.pair(kPolar, k, attempt++, u1, u2);
+        xg = __dsub_rn(__dmul_rn(u1, 2.0), 1.0);
+        yg = __dsub_rn(__dmul_rn(u2, 2.0), 1.0);
+        s = __dadd_rn(__dmul_rn(xg, xg), __dmul_rn(yg, yg));
+    } while (s <= 0.0 || s >= 1.0);
+}
 
 // one visit_fn(T) draw for coordinate k, Philox source: polar rejection loop        :94-102
 __device__ __forceinline__ double visit_sample_philox(const PhiloxRng &rng, uint32_t k,

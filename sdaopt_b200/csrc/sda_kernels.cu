@@ -19,50 +19,79 @@
 namespace sda {
 
 // MarkovChain.local_search                                                        :236-273
-__device__ inline void markov_local_search(const DeviceArgs &a, ChainState &st, LsWork &w,
+// The chain state and the L-BFGS-B work descriptor are handed to the (noinline) minimiser as
+// copies so that the annealing loop's own state never has its address taken and stays in registers.
+__device__ __forceinline__ int call_local_search(const DeviceArgs &a, ChainState &st, double *ls_slot,
+                                                 const double *x_start, double *xe, const double *lo,
+                                                 const double *up, double &e, double *&x_out, int lane)
+{
+    ChainState tmp = st;
+    LsWork w;
+    w.bind(ls_slot, a.dim);
+    const int ok = ofw_local_search(a, tmp, w, x_start, xe, lo, up, e, lane);
+    st = tmp;
+    x_out = w.x;
+    return ok;
+}
+
+__device__ inline void markov_local_search(const DeviceArgs &a, ChainState &st, double *ls_slot,
                                            double *x_cur, double *x_vis, const double *lo,
                                            const double *up, double *xbest, double *xmin, int lane)
 {
     const int dim = a.dim;
     double e;
+    double *wx = nullptr;
     if (st.state_improved) {
-        ofw_local_search(a, st, w, xbest, x_vis, lo, up, e, lane);
+        call_local_search(a, st, ls_slot, xbest, x_vis, lo, up, e, wx, lane);
         if (st.stop) return;
         if (e < st.ebest) {
             st.not_improved_idx = 0;
             st.ebest = e;
-            copy_vec(xbest, w.x, dim, lane);
+            copy_vec(xbest, wx, dim, lane);
             st.e_cur = e;
-            copy_vec(x_cur, w.x, dim, lane);
+            copy_vec(x_cur, wx, dim, lane);
             __syncwarp();
             return;
         }
     }
     // :254-258 is dead code in the reference (K = 100*D is never < 90*D): no uniform is drawn
     if (st.not_improved_idx >= st.not_improved_max_idx) {
-        const int ok = ofw_local_search(a, st, w, xmin, x_vis, lo, up, e, lane);
+        const int ok = call_local_search(a, st, ls_slot, xmin, x_vis, lo, up, e, wx, lane);
         if (st.stop) return;
-        if (ok) copy_vec(xmin, w.x, dim, lane);
+        if (ok) copy_vec(xmin, wx, dim, lane);
         st.emin = e;
         st.not_improved_idx = 0;
         st.not_improved_max_idx = dim;
         if (e < st.ebest) {
             st.ebest = st.emin;
-            copy_vec(xbest, w.x, dim, lane);
+            copy_vec(xbest, wx, dim, lane);
             st.e_cur = e;
-            copy_vec(x_cur, w.x, dim, lane);
+            copy_vec(x_cur, wx, dim, lane);
         }
         __syncwarp();
     }
 }
 
+template <bool TAPE>
+__device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState &st, Rng<TAPE> &rng,
+                                                 double *x_cur, const double *lo, const double *up,
+                                                 const double *x0, double *xbest, int lane)
+{
+    ChainState tmp = st;
+    Rng<TAPE> r2 = rng;
+    const int err = energy_reset<TAPE>(a, tmp, r2, x_cur, lo, up, x0, xbest, lane);
+    st = tmp;
+    rng = r2;
+    return err;
+}
+
 // SDARunner.__init__ + search + result for one chain                               :357-428
 template <bool TAPE>
 __device__ inline void run_chain(const DeviceArgs &a, long long chain, double *x_cur, double *x_vis,
-                                 double *sv, const double *lo, const double *up, double *ls_slot,
-                                 int lane)
+                                 double *sv, const Box &bx, double *ls_slot, int lane)
 {
     const int dim = a.dim;
+    const double *lo = bx.lo, *up = bx.up;
     ChainState st;
     st.e_cur = st.ebest = st.emin = 0.0;
     st.not_improved_idx = 0; st.not_improved_max_idx = 1000;     // :186-187
@@ -83,11 +112,9 @@ __device__ inline void run_chain(const DeviceArgs &a, long long chain, double *x
     }
     double *xbest = a.out.x + chain * dim;
     double *xmin = a.xmin + chain * dim;
-    LsWork w;
-    w.bind(ls_slot, dim);
 
-    int err = energy_reset<TAPE>(a, st, rng, x_cur, lo, up,
-                                 a.x0 ? a.x0 + chain * dim : nullptr, xbest, lane);
+    int err = call_energy_reset<TAPE>(a, st, rng, x_cur, lo, up,
+                                      a.x0 ? a.x0 + chain * dim : nullptr, xbest, lane);
     long long iter = 0;
     if (!err && !st.stop) {
         st.emin = st.e_cur;                                      // :176-177
@@ -103,16 +130,16 @@ __device__ inline void run_chain(const DeviceArgs &a, long long chain, double *x
                 if constexpr (!TAPE) { rng.p.iter = (uint32_t)iter; rng.p.j = 0xFFFFFFu; }
                 if (iter == a.maxiter) { max_steps_reached = true; break; }          // :404-406
                 if (temperature < a.temperature_restart) {                             // :408-410
-                    err = energy_reset<TAPE>(a, st, rng, x_cur, lo, up, nullptr, xbest, lane);
+                    err = call_energy_reset<TAPE>(a, st, rng, x_cur, lo, up, nullptr, xbest, lane);
                     break;
                 }
-                markov_run<TAPE>(a, st, rng, chain, i, temperature, sigmax, x_cur, x_vis, sv, lo,
-                                 up, xbest, xmin, lane);                               // :412
+                markov_run<TAPE>(a, st, rng, chain, i, temperature, sigmax, x_cur, x_vis, sv, bx,
+                                 xbest, xmin, lane);                                   // :412
                 if (st.stop) break;
                 if constexpr (TAPE) { if (rng.t.exhausted) break; }
                 if ((double)st.ncall >= a.maxfun) break;                               // :413-414
                 if (!a.pure_sa) {                                                      // :415-418
-                    markov_local_search(a, st, w, x_cur, x_vis, lo, up, xbest, xmin, lane);
+                    markov_local_search(a, st, ls_slot, x_cur, x_vis, lo, up, xbest, xmin, lane);
                     if (st.stop) break;
                     if ((double)st.ncall >= a.maxfun) break;
                 }
@@ -137,9 +164,12 @@ __device__ inline void run_chain(const DeviceArgs &a, long long chain, double *x
     }
 }
 
-// shared memory: lower[D] upper[D] | per warp: x_cur[D] x_vis[D] sv[D]
+// shared memory: lower[D] upper[D] range[D] 1/range[D] | per warp: x_cur[D] x_vis[D] sv[D]
+#ifndef SDA_ANNEAL_MIN_BLOCKS
+#define SDA_ANNEAL_MIN_BLOCKS 2
+#endif
 template <bool TAPE>
-__global__ void __launch_bounds__(256) sda_anneal_kernel(const DeviceArgs a)
+__global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(const DeviceArgs a)
 {
     extern __shared__ double smem[];
     const int dim = a.dim;
@@ -148,9 +178,17 @@ __global__ void __launch_bounds__(256) sda_anneal_kernel(const DeviceArgs a)
     const int warps_per_block = blockDim.x >> 5;
     double *lo = smem;
     double *up = smem + dim;
-    for (int k = threadIdx.x; k < dim; k += blockDim.x) { lo[k] = a.lower[k]; up[k] = a.upper[k]; }
+    double *rg = smem + 2 * dim;
+    double *irg = smem + 3 * dim;
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) {
+        const double l = a.lower[k], u = a.upper[k];
+        lo[k] = l; up[k] = u;
+        rg[k] = __dsub_rn(u, l);                       // self.b_range = ub - lb      :35
+        irg[k] = __ddiv_rn(1.0, rg[k]);
+    }
     __syncthreads();
-    double *x_cur = smem + 2 * dim + (size_t)warp * 3 * dim;
+    const Box bx = { lo, up, rg, irg };
+    double *x_cur = smem + 4 * dim + (size_t)warp * 3 * dim;
     double *x_vis = x_cur + dim;
     double *sv = x_vis + dim;
     const long long slot = (long long)blockIdx.x * warps_per_block + warp;
@@ -160,7 +198,7 @@ __global__ void __launch_bounds__(256) sda_anneal_kernel(const DeviceArgs a)
         if (lane == 0) c = atomicAdd(a.work_counter, 1ULL);
         c = __shfl_sync(SDA_FULL_MASK, c, 0);
         if ((long long)c >= a.n_chains) break;
-        run_chain<TAPE>(a, (long long)c, x_cur, x_vis, sv, lo, up, ls_slot, lane);
+        run_chain<TAPE>(a, (long long)c, x_cur, x_vis, sv, bx, ls_slot, lane);
         __syncwarp();
     }
 }
@@ -198,7 +236,7 @@ __global__ void sda_visiting_kernel(DeviceArgs a, const double *x, long long ste
             double v = sv[k];
             if (v > kTailLimit) v = __dmul_rn(kTailLimit, us);
             else if (v < -kTailLimit) v = __dmul_rn(-kTailLimit, ls);
-            x_visit[k] = wrap_coord(__dadd_rn(v, x[k]), a.lower[k], __dsub_rn(a.upper[k], a.lower[k]));
+            { const double rg = __dsub_rn(a.upper[k], a.lower[k]); x_visit[k] = wrap_coord(__dadd_rn(v, x[k]), a.lower[k], rg, __ddiv_rn(1.0, rg)); }
         }
     } else {
         const int index = (int)(step - dim);
@@ -208,8 +246,10 @@ __global__ void sda_visiting_kernel(DeviceArgs a, const double *x, long long ste
         else if (visit < -kTailLimit) visit = __dmul_rn(-kTailLimit, rng.next());
         __syncwarp();
         if (lane == 0)
-            x_visit[index] = wrap_coord(__dadd_rn(visit, x[index]), a.lower[index],
-                                        __dsub_rn(a.upper[index], a.lower[index]));
+        {
+            const double rg = __dsub_rn(a.upper[index], a.lower[index]);
+            x_visit[index] = wrap_coord(__dadd_rn(visit, x[index]), a.lower[index], rg, __ddiv_rn(1.0, rg));
+        }
     }
     if (lane == 0) *tape_used = rng.exhausted ? -1 : rng.pos;
 }
@@ -377,14 +417,14 @@ static int plan_launch(int dim, long long n_chains, LaunchPlan *lp)
     e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
     int wpb = 8;
-    while (wpb > 1 && (size_t)(2 + 3 * wpb) * dim * sizeof(double) > (size_t)smem_max) wpb >>= 1;
-    size_t smem = (size_t)(2 + 3 * wpb) * dim * sizeof(double);
+    while (wpb > 1 && (size_t)(4 + 3 * wpb) * dim * sizeof(double) > (size_t)smem_max) wpb >>= 1;
+    size_t smem = (size_t)(4 + 3 * wpb) * dim * sizeof(double);
     if (smem > (size_t)smem_max) return SDA_E_UNSUPPORTED;
     // resident blocks per SM: bounded by shared memory and by 2048 threads
     int bps = (int)((size_t)(smem_max) / (smem + 1024));
     if (bps < 1) bps = 1;
     int max_bps = 64 / wpb; // 64 warps per SM
-    if (max_bps > 4) max_bps = 4; // register budget: 4 x 256 threads
+    if (max_bps > SDA_ANNEAL_MIN_BLOCKS * 8 / wpb) max_bps = SDA_ANNEAL_MIN_BLOCKS * 8 / wpb; // register budget
     if (bps > max_bps) bps = max_bps;
     long long want = (n_chains + wpb - 1) / wpb;
     long long blocks = (long long)sms * bps;
