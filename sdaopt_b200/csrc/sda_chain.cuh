@@ -57,10 +57,12 @@ struct ChainState {
 };
 
 // the callable handed to sda(): objective + suite monitor (bench.py:292-321)
+template <bool INLINE_EVAL>
 __device__ __forceinline__ double call_func(const DeviceArgs &a, ChainState &st, const double *x,
                                             int lane)
 {
-    const double res = eval_objective(a.functor, x, a.dim, a.params, lane);
+    const double res = INLINE_EVAL ? eval_objective(a.functor, x, a.dim, a.params, lane)
+                                   : eval_objective_ool(a.functor, x, a.dim, a.params, lane);
     if (a.max_calls > 0 && !st.stop) {
         st.mon_calls += 1;                              // bench.py:300
         if (st.mon_calls >= a.max_calls) {              // bench.py:301-304
@@ -76,12 +78,13 @@ __device__ __forceinline__ double call_func(const DeviceArgs &a, ChainState &st,
 }
 
 // ObjectiveFunWrapper.func_wrapper                                                :321-323
+template <bool IN_LS>
 __device__ __forceinline__ double func_wrapper(const DeviceArgs &a, ChainState &st,
-                                               const double *x, int lane, bool in_ls)
+                                               const double *x, int lane)
 {
     st.ncall += 1;
-    if (in_ls) st.ncall_ls += 1;
-    return call_func(a, st, x, lane);
+    if (IN_LS) st.ncall_ls += 1;
+    return call_func<!IN_LS>(a, st, x, lane);
 }
 
 __device__ __forceinline__ void copy_vec(double *dst, const double *src, int dim, int lane)
@@ -129,7 +132,7 @@ __device__ __noinline__ int energy_reset(const DeviceArgs &a, ChainState &st, Rn
     int reinit = 0;
     for (;;) {
         bool done = false;
-        st.e_cur = call_func(a, st, x_cur, lane);       // owf.func: not counted      :144
+        st.e_cur = call_func<false>(a, st, x_cur, lane); // owf.func: not counted      :144
         if (st.stop) return 0;
         if (st.e_cur >= kBigValue || isnan(st.e_cur)) {
             if (reinit >= kMaxReinit) return SDA_CHAIN_REINIT_FAILED;
@@ -300,7 +303,7 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
         }
         if constexpr (TAPE) { if (rng.t.exhausted) return; }
         // ---- K3: objective                                                      :203
-        const double e = func_wrapper(a, st, x_vis, lane, false);
+        const double e = func_wrapper<false>(a, st, x_vis, lane);
         if (st.stop) return;
         // ---- K4: acceptance.  The uniform is drawn only when e >= E_cur          :216
         double r = 0.0;

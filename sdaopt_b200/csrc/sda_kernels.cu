@@ -22,12 +22,12 @@ namespace sda {
 // The chain state and the L-BFGS-B work descriptor are handed to the (noinline) minimiser as
 // copies so that the annealing loop's own state never has its address taken and stays in registers.
 __device__ __forceinline__ int call_local_search(const DeviceArgs &a, ChainState &st, double *ls_slot,
-                                                 const double *x_start, double *xe, const double *lo,
+                                                 double *ls_smem, const double *x_start, double *xe, const double *lo,
                                                  const double *up, double &e, double *&x_out, int lane)
 {
     ChainState tmp = st;
     LsWork w;
-    w.bind(ls_slot, a.dim);
+    w.bind(ls_slot, ls_smem, a.dim);
     const int ok = ofw_local_search(a, tmp, w, x_start, xe, lo, up, e, lane);
     st = tmp;
     x_out = w.x;
@@ -35,14 +35,14 @@ __device__ __forceinline__ int call_local_search(const DeviceArgs &a, ChainState
 }
 
 __device__ inline void markov_local_search(const DeviceArgs &a, ChainState &st, double *ls_slot,
-                                           double *x_cur, double *x_vis, const double *lo,
+                                           double *ls_smem, double *x_cur, double *x_vis, const double *lo,
                                            const double *up, double *xbest, double *xmin, int lane)
 {
     const int dim = a.dim;
     double e;
     double *wx = nullptr;
     if (st.state_improved) {
-        call_local_search(a, st, ls_slot, xbest, x_vis, lo, up, e, wx, lane);
+        call_local_search(a, st, ls_slot, ls_smem, xbest, x_vis, lo, up, e, wx, lane);
         if (st.stop) return;
         if (e < st.ebest) {
             st.not_improved_idx = 0;
@@ -56,7 +56,7 @@ __device__ inline void markov_local_search(const DeviceArgs &a, ChainState &st, 
     }
     // :254-258 is dead code in the reference (K = 100*D is never < 90*D): no uniform is drawn
     if (st.not_improved_idx >= st.not_improved_max_idx) {
-        const int ok = call_local_search(a, st, ls_slot, xmin, x_vis, lo, up, e, wx, lane);
+        const int ok = call_local_search(a, st, ls_slot, ls_smem, xmin, x_vis, lo, up, e, wx, lane);
         if (st.stop) return;
         if (ok) copy_vec(xmin, wx, dim, lane);
         st.emin = e;
@@ -88,7 +88,7 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 // SDARunner.__init__ + search + result for one chain                               :357-428
 template <bool TAPE>
 __device__ inline void run_chain(const DeviceArgs &a, long long chain, double *x_cur, double *x_vis,
-                                 double *sv, const Box &bx, double *ls_slot, int lane)
+                                 double *sv, const Box &bx, double *ls_slot, double *ls_smem, int lane)
 {
     const int dim = a.dim;
     const double *lo = bx.lo, *up = bx.up;
@@ -139,7 +139,7 @@ __device__ inline void run_chain(const DeviceArgs &a, long long chain, double *x
                 if constexpr (TAPE) { if (rng.t.exhausted) break; }
                 if ((double)st.ncall >= a.maxfun) break;                               // :413-414
                 if (!a.pure_sa) {                                                      // :415-418
-                    markov_local_search(a, st, ls_slot, x_cur, x_vis, lo, up, xbest, xmin, lane);
+                    markov_local_search(a, st, ls_slot, ls_smem, x_cur, x_vis, lo, up, xbest, xmin, lane);
                     if (st.stop) break;
                     if ((double)st.ncall >= a.maxfun) break;
                 }
@@ -193,12 +193,14 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
     double *sv = x_vis + dim;
     const long long slot = (long long)blockIdx.x * warps_per_block + warp;
     double *ls_slot = a.ls_work ? a.ls_work + slot * a.ls_stride : nullptr;
+    // per-warp shared-memory block of the L-BFGS-B middle matrices (only with local search on)
+    double *ls_smem = smem + 4 * dim + (size_t)warps_per_block * 3 * dim + (size_t)warp * ls_smem_doubles();
     for (;;) {
         unsigned long long c = 0;
         if (lane == 0) c = atomicAdd(a.work_counter, 1ULL);
         c = __shfl_sync(SDA_FULL_MASK, c, 0);
         if ((long long)c >= a.n_chains) break;
-        run_chain<TAPE>(a, (long long)c, x_cur, x_vis, sv, bx, ls_slot, lane);
+        run_chain<TAPE>(a, (long long)c, x_cur, x_vis, sv, bx, ls_slot, ls_smem, lane);
         __syncwarp();
     }
 }
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(128) sda_local_search_kernel(DeviceArgs a, con
     const long long slot = (long long)blockIdx.x * wpb + warp;
     const long long nslots = (long long)gridDim.x * wpb;
     LsWork w;
-    w.bind(a.ls_work + slot * a.ls_stride, dim);
+    w.bind(a.ls_work + slot * a.ls_stride, smem + (size_t)(2 + wpb) * dim + (size_t)warp * ls_smem_doubles(), dim);
     for (long long p = slot; p < n; p += nslots) {
         ChainState st;
         memset(&st, 0, sizeof(st));
@@ -407,7 +409,7 @@ struct LaunchPlan {
     long long slots;
 };
 
-static int plan_launch(int dim, long long n_chains, LaunchPlan *lp)
+static int plan_launch(int dim, long long n_chains, int pure_sa, LaunchPlan *lp)
 {
     int dev = 0, sms = 0, smem_max = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -417,8 +419,9 @@ static int plan_launch(int dim, long long n_chains, LaunchPlan *lp)
     e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
     int wpb = 8;
-    while (wpb > 1 && (size_t)(4 + 3 * wpb) * dim * sizeof(double) > (size_t)smem_max) wpb >>= 1;
-    size_t smem = (size_t)(4 + 3 * wpb) * dim * sizeof(double);
+    const size_t ls_per_warp = pure_sa ? 0 : (size_t)sda::ls_smem_doubles() * sizeof(double);
+    while (wpb > 1 && (size_t)(4 + 3 * wpb) * dim * sizeof(double) + wpb * ls_per_warp > (size_t)smem_max) wpb >>= 1;
+    size_t smem = (size_t)(4 + 3 * wpb) * dim * sizeof(double) + wpb * ls_per_warp;
     if (smem > (size_t)smem_max) return SDA_E_UNSUPPORTED;
     // resident blocks per SM: bounded by shared memory and by 2048 threads
     int bps = (int)((size_t)(smem_max) / (smem + 1024));
@@ -493,7 +496,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     if (c->rng_mode == SDA_RNG_TAPE && (!tape || tape_len <= 0)) return SDA_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     LaunchPlan lp;
-    rc = plan_launch(p->dim, n_chains, &lp);
+    rc = plan_launch(p->dim, n_chains, c->pure_sa, &lp);
     if (rc) return rc;
     size_t off_temp, off_sig, off_xmin, off_ls;
     long long ls_stride;
@@ -720,8 +723,9 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
     int wpb = 4;
     int smem_max = 0;
     CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    while (wpb > 1 && (size_t)(2 + wpb) * D * 8 > (size_t)smem_max) wpb >>= 1;
-    const size_t smem = (size_t)(2 + wpb) * D * 8;
+    const size_t lsb = (size_t)sda::ls_smem_doubles() * 8;
+    while (wpb > 1 && (size_t)(2 + wpb) * D * 8 + wpb * lsb > (size_t)smem_max) wpb >>= 1;
+    const size_t smem = (size_t)(2 + wpb) * D * 8 + wpb * lsb;
     long long blocks = (n + wpb - 1) / wpb;
     if (blocks > 148 * 4) blocks = 148 * 4;
     const long long stride = (sda::ls_workspace_doubles(p->dim) + 31) & ~31LL;

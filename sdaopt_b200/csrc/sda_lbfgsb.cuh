@@ -29,12 +29,16 @@ constexpr int kLsMaxls = 100;
 constexpr int kLsMaxfun = 15000;
 constexpr double kGradEps = 1.e-6;   // self.reps                                   :315
 
+// global (L1/L2) part of a warp's workspace: ws, wy | z r d t xp g x xl gl | 3 int arrays
 __host__ __device__ inline long long ls_workspace_doubles(int n)
 {
     const int m = kLsM;
-    // ws, wy | sy ss wt | wn snd | z r d t xp g x xl gl | wa | 3 int arrays (as 2n doubles)
-    return 2LL * m * n + 3LL * m * m + 8LL * m * m + 9LL * n + 8LL * m + 2LL * n + 8;
+    return 2LL * m * n + 9LL * n + 2LL * n + 8;
 }
+// shared-memory part: sy ss wt (m x m) | wn snd (2m x 2m) | wa (8m).  These are updated in place
+// element by element (Cholesky, triangular solves, running sums); through global memory every
+// read-after-write would pay an L2 round trip because stores write through and drop the L1 line.
+__host__ __device__ constexpr int ls_smem_doubles() { return 3 * kLsM * kLsM + 8 * kLsM * kLsM + 8 * kLsM; }
 
 struct LsWork {
     int n;
@@ -45,18 +49,19 @@ struct LsWork {
     double fl;
     int cache_valid;
     int *index, *iwhere, *indx2;
-    __device__ void bind(double *base, int n_)
+    __device__ void bind(double *base, double *sbase, int n_)
     {
         const int m = kLsM;
         n = n_;
-        double *q = base;
-        ws = q; q += (long long)m * n;  wy = q; q += (long long)m * n;
+        double *q = sbase;
         sy = q; q += m * m;  ss = q; q += m * m;  wt = q; q += m * m;
         wn = q; q += 4 * m * m;  snd = q; q += 4 * m * m;
+        wa = q;
+        q = base;
+        ws = q; q += (long long)m * n;  wy = q; q += (long long)m * n;
         z = q; q += n;  r = q; q += n;  d = q; q += n;  t = q; q += n;  xp = q; q += n;
         g = q; q += n;  x = q; q += n;  xl = q; q += n;  gl = q; q += n;
         cache_valid = 0;
-        wa = q; q += 8 * m;
         index = reinterpret_cast<int *>(q);
         iwhere = index + n;
         indx2 = iwhere + n;
@@ -73,12 +78,15 @@ struct LsWork {
 #define LWN1(i, j) w.snd[((j) - 1) * 2 * m + ((i) - 1)]
 
 // ---- dense helpers on warp-uniform data (executed redundantly by every lane) -----------------
-__device__ inline int chol_upper(double *a, int lda, int nn)
+__device__ __noinline__ int chol_upper(double *a, int lda, int nn)
 {
+    #pragma unroll 1
     for (int j = 1; j <= nn; ++j) {
         double s = 0.0;
+        #pragma unroll 1
         for (int k = 1; k <= j - 1; ++k) {
             double dot = 0.0;
+            #pragma unroll 1
             for (int i = 1; i <= k - 1; ++i) dot += a[(k - 1) * lda + i - 1] * a[(j - 1) * lda + i - 1];
             double tt = a[(j - 1) * lda + k - 1] - dot;
             tt = tt / a[(k - 1) * lda + k - 1];
@@ -92,22 +100,27 @@ __device__ inline int chol_upper(double *a, int lda, int nn)
     return 0;
 }
 
-__device__ inline int tri_solve_upper(const double *t, int ldt, int nn, double *b, int trans)
+__device__ __noinline__ int tri_solve_upper(const double *t, int ldt, int nn, double *b, int trans)
 {
+    #pragma unroll 1
     for (int j = 1; j <= nn; ++j)
         if (t[(j - 1) * ldt + j - 1] == 0.0) return j;
     if (trans) {
         b[0] = b[0] / t[0];
+        #pragma unroll 1
         for (int j = 2; j <= nn; ++j) {
             double dot = 0.0;
+            #pragma unroll 1
             for (int i = 1; i <= j - 1; ++i) dot += t[(j - 1) * ldt + i - 1] * b[i - 1];
             b[j - 1] = (b[j - 1] - dot) / t[(j - 1) * ldt + j - 1];
         }
     } else {
         b[nn - 1] = b[nn - 1] / t[(nn - 1) * ldt + nn - 1];
+        #pragma unroll 1
         for (int jj = 2; jj <= nn; ++jj) {
             const int j = nn - jj + 1;
             const double temp = -b[j];
+            #pragma unroll 1
             for (int i = 1; i <= j; ++i) b[i - 1] += temp * t[j * ldt + i - 1];
             b[j - 1] = b[j - 1] / t[(j - 1) * ldt + j - 1];
         }
@@ -116,38 +129,46 @@ __device__ inline int tri_solve_upper(const double *t, int ldt, int nn, double *
 }
 
 // product of the 2m x 2m middle matrix of the compact representation with v
-__device__ inline int ls_bmv(LsWork &w, int col, const double *v, double *p)
+__device__ __noinline__ int ls_bmv(LsWork &w, int col, const double *v, double *p)
 {
     const int m = kLsM;
     if (col == 0) return 0;
     p[col] = v[col];
+    #pragma unroll 1
     for (int i = 2; i <= col; ++i) {
         const int i2 = col + i;
         double sum = 0.0;
+        #pragma unroll 1
         for (int k = 1; k <= i - 1; ++k) sum += LSY(i, k) * v[k - 1] / LSY(k, k);
         p[i2 - 1] = v[i2 - 1] + sum;
     }
     if (tri_solve_upper(w.wt, m, col, p + col, 1)) return 1;
+    #pragma unroll 1
     for (int i = 1; i <= col; ++i) p[i - 1] = v[i - 1] / sqrt(LSY(i, i));
     if (tri_solve_upper(w.wt, m, col, p + col, 0)) return 1;
+    #pragma unroll 1
     for (int i = 1; i <= col; ++i) p[i - 1] = -p[i - 1] / sqrt(LSY(i, i));
+    #pragma unroll 1
     for (int i = 1; i <= col; ++i) {
         double sum = 0.0;
+        #pragma unroll 1
         for (int k = i + 1; k <= col; ++k) sum += LSY(k, i) * p[col + k - 1] / LSY(i, i);
         p[i - 1] += sum;
     }
     return 0;
 }
 
-__device__ inline void heap_least(int nn, double *t, int *iorder, int iheap)
+__device__ __noinline__ void heap_least(int nn, double *t, int *iorder, int iheap)
 {
     double *T = t - 1;
     int *IO = iorder - 1;
     if (iheap == 0) {
+        #pragma unroll 1
         for (int k = 2; k <= nn; ++k) {
             const double ddum = T[k];
             const int indxin = IO[k];
             int i = k;
+            #pragma unroll 1
             while (i > 1) {
                 const int j = i / 2;
                 if (ddum < T[j]) { T[i] = T[j]; IO[i] = IO[j]; i = j; }
@@ -162,6 +183,7 @@ __device__ inline void heap_least(int nn, double *t, int *iorder, int iheap)
         const int indxou = IO[1];
         const double ddum = T[nn];
         const int indxin = IO[nn];
+        #pragma unroll 1
         for (;;) {
             int j = i + i;
             if (j <= nn - 1) {
@@ -176,8 +198,9 @@ __device__ inline void heap_least(int nn, double *t, int *iorder, int iheap)
 }
 
 // generalized Cauchy point (warp-uniform, serial: the breakpoint bookkeeping is order dependent)
-__device__ inline int ls_cauchy(LsWork &w, const double *x, const double *l, const double *u,
-                                const double *g, double theta, int col, int head, double sbgnrm)
+__device__ __noinline__ int ls_cauchy(LsWork &w, const double *x, const double *l, const double *u,
+                                const double *g, double theta, int col, int head, double sbgnrm,
+                                int lane)
 {
     const int n = w.n, m = kLsM;
     int *iorder = w.indx2, *iwhere = w.iwhere;
@@ -187,7 +210,9 @@ __device__ inline int ls_cauchy(LsWork &w, const double *x, const double *l, con
     int bnded = 1, nfree = n + 1, nbreak = 0, ibkmin = 0;
     double bkmin = 0.0, f1 = 0.0;
     const int col2 = 2 * col;
+    #pragma unroll 1
     for (int i = 0; i < col2; ++i) p[i] = 0.0;
+    #pragma unroll 1
     for (int i = 1; i <= n; ++i) {
         const double neggi = -g[i - 1];
         const double tl = x[i - 1] - l[i - 1];
@@ -200,17 +225,11 @@ __device__ inline int ls_cauchy(LsWork &w, const double *x, const double *l, con
             else { if (fabs(neggi) <= 0.0) iw = -3; }
             iwhere[i - 1] = iw;
         }
-        int pointr = head;
         if (iwhere[i - 1] != 0 && iwhere[i - 1] != -1) {
             d[i - 1] = 0.0;
         } else {
             d[i - 1] = neggi;
             f1 -= neggi * neggi;
-            for (int j = 1; j <= col; ++j) {
-                p[j - 1] += LWY(i, pointr) * neggi;
-                p[col + j - 1] += LWS(i, pointr) * neggi;
-                pointr = pointr % m + 1;
-            }
             if (neggi < 0.0) {
                 nbreak++; iorder[nbreak - 1] = i; t[nbreak - 1] = tl / (-neggi);
                 if (nbreak == 1 || t[nbreak - 1] < bkmin) { bkmin = t[nbreak - 1]; ibkmin = nbreak; }
@@ -223,15 +242,30 @@ __device__ inline int ls_cauchy(LsWork &w, const double *x, const double *l, con
             }
         }
     }
-    if (theta != 1.0) for (int j = 0; j < col; ++j) p[col + j] *= theta;
+    // p = W' d: lane j owns p[j] (columns of Y for j < col, of S for j >= col); d is zero on the
+    // variables that do not move, so the sum runs over all i in the published order
+    __syncwarp();
+    if (lane < col2) {
+        const int jj = lane < col ? lane : lane - col;
+        const int pointr = (head - 1 + jj) % m + 1;
+        const double *wc = lane < col ? &LWY(1, pointr) : &LWS(1, pointr);
+        double acc = 0.0;
+        #pragma unroll 1
+        for (int i = 0; i < n; ++i) acc += wc[i] * d[i];
+        p[lane] = (lane >= col && theta != 1.0) ? acc * theta : acc;
+    }
+    __syncwarp();
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) xcp[i] = x[i];
     if (nbreak == 0 && nfree == n + 1) return 0;
+    #pragma unroll 1
     for (int j = 0; j < col2; ++j) c[j] = 0.0;
     double f2 = -theta * f1;
     const double f2_org = f2;
     if (col > 0) {
         if (ls_bmv(w, col, p, v)) return 1;
         double dot = 0.0;
+        #pragma unroll 1
         for (int j = 0; j < col2; ++j) dot += v[j] * p[j];
         f2 -= dot;
     }
@@ -241,6 +275,7 @@ __device__ inline int ls_cauchy(LsWork &w, const double *x, const double *l, con
     if (nbreak != 0) {
         int nleft = nbreak, iter = 1;
         double tj = 0.0;
+        #pragma unroll 1
         for (;;) {
             const double tj0 = tj;
             int ibp;
@@ -267,8 +302,10 @@ __device__ inline int ls_cauchy(LsWork &w, const double *x, const double *l, con
             f1 = f1 + dt * f2 + dibp2 - theta * dibp * zibp;
             f2 = f2 - theta * dibp2;
             if (col > 0) {
+                #pragma unroll 1
                 for (int j = 0; j < col2; ++j) c[j] += dt * p[j];
                 int pointr = head;
+                #pragma unroll 1
                 for (int j = 1; j <= col; ++j) {
                     wbp[j - 1] = LWY(ibp, pointr);
                     wbp[col + j - 1] = theta * LWS(ibp, pointr);
@@ -276,7 +313,9 @@ __device__ inline int ls_cauchy(LsWork &w, const double *x, const double *l, con
                 }
                 if (ls_bmv(w, col, wbp, v)) return 1;
                 double wmc = 0.0, wmp = 0.0, wmw = 0.0;
+                #pragma unroll 1
                 for (int j = 0; j < col2; ++j) { wmc += c[j] * v[j]; wmp += p[j] * v[j]; wmw += wbp[j] * v[j]; }
+                #pragma unroll 1
                 for (int j = 0; j < col2; ++j) p[j] -= dibp * wbp[j];
                 f1 += dibp * wmc;
                 f2 += 2.0 * dibp * wmp - dibp2 * wmw;
@@ -291,23 +330,26 @@ __device__ inline int ls_cauchy(LsWork &w, const double *x, const double *l, con
     if (!skip_tail) {
         if (dtm <= 0.0) dtm = 0.0;
         tsum += dtm;
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) xcp[i] += tsum * d[i];
     }
     if (col > 0) for (int j = 0; j < col2; ++j) c[j] += dtm * p[j];
     return 0;
 }
 
-__device__ inline void ls_freev(LsWork &w, int &nfree, int &nenter, int &ileave, int &wrk,
+__device__ __noinline__ void ls_freev(LsWork &w, int &nfree, int &nenter, int &ileave, int &wrk,
                                 int updatd, int iter)
 {
     const int n = w.n;
     int *index = w.index, *indx2 = w.indx2, *iwhere = w.iwhere;
     nenter = 0; ileave = n + 1;
     if (iter > 0) {
+        #pragma unroll 1
         for (int i = 1; i <= nfree; ++i) {
             const int k = index[i - 1];
             if (iwhere[k - 1] > 0) { ileave--; indx2[ileave - 1] = k; }
         }
+        #pragma unroll 1
         for (int i = 1 + nfree; i <= n; ++i) {
             const int k = index[i - 1];
             if (iwhere[k - 1] <= 0) { nenter++; indx2[nenter - 1] = k; }
@@ -316,6 +358,7 @@ __device__ inline void ls_freev(LsWork &w, int &nfree, int &nenter, int &ileave,
     wrk = (ileave < n + 1) || (nenter > 0) || updatd;
     nfree = 0;
     int iact = n + 1;
+    #pragma unroll 1
     for (int i = 1; i <= n; ++i) {
         if (iwhere[i - 1] <= 0) { nfree++; index[nfree - 1] = i; }
         else { iact--; index[iact - 1] = i; }
@@ -327,6 +370,7 @@ __device__ __forceinline__ double list_dot(const double *A, const double *B, con
                                            int e, int lane)
 {
     double s = 0.0;
+    #pragma unroll 1
     for (int k = b + lane; k <= e; k += SDA_WARP) {
         const int k1 = list[k - 1] - 1;
         s += A[k1] * B[k1];
@@ -335,7 +379,7 @@ __device__ __forceinline__ double list_dot(const double *A, const double *B, con
 }
 
 // LEL^T factorisation of the indefinite K matrix of the subspace problem
-__device__ inline int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int iupdat, int updatd,
+__device__ __noinline__ int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int iupdat, int updatd,
                                double theta, int col, int head, int lane)
 {
     const int n = w.n, m = kLsM;
@@ -343,10 +387,14 @@ __device__ inline int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int 
     int upcl;
     if (updatd) {
         if (iupdat > m) {
+            #pragma unroll 1
             for (int jy = 1; jy <= m - 1; ++jy) {
                 const int js = m + jy;
+                #pragma unroll 1
                 for (int i = 0; i < m - jy; ++i) LWN1(jy + i, jy) = LWN1(jy + 1 + i, jy + 1);
+                #pragma unroll 1
                 for (int i = 0; i < m - jy; ++i) LWN1(js + i, js) = LWN1(js + 1 + i, js + 1);
+                #pragma unroll 1
                 for (int i = 0; i < m - 1; ++i) LWN1(m + 1 + i, jy) = LWN1(m + 2 + i, jy + 1);
             }
         }
@@ -355,6 +403,7 @@ __device__ inline int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int 
         int ipntr = head + col - 1;
         if (ipntr > m) ipntr -= m;
         int jpntr = head;
+        #pragma unroll 1
         for (int jy = 1; jy <= col; ++jy) {
             const int js = m + jy;
             const double temp1 = list_dot(&LWY(1, ipntr), &LWY(1, jpntr), ind, pbegin, pend, lane);
@@ -367,6 +416,7 @@ __device__ inline int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int 
         jpntr = head + col - 1;
         if (jpntr > m) jpntr -= m;
         ipntr = head;
+        #pragma unroll 1
         for (int i = 1; i <= col; ++i) {
             const int is2 = m + i;
             const double temp3 = list_dot(&LWS(1, ipntr), &LWY(1, jpntr), ind, pbegin, pend, lane);
@@ -379,9 +429,11 @@ __device__ inline int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int 
     }
     if (nenter > 0 || ileave <= n) {
         int ipntr = head;
+        #pragma unroll 1
         for (int iy = 1; iy <= upcl; ++iy) {
             const int is = m + iy;
             int jpntr = head;
+            #pragma unroll 1
             for (int jy = 1; jy <= iy; ++jy) {
                 const int js = m + jy;
                 const double temp1 = list_dot(&LWY(1, ipntr), &LWY(1, jpntr), indx2, 1, nenter, lane);
@@ -395,8 +447,10 @@ __device__ inline int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int 
             ipntr = ipntr % m + 1;
         }
         ipntr = head;
+        #pragma unroll 1
         for (int is = m + 1; is <= m + upcl; ++is) {
             int jpntr = head;
+            #pragma unroll 1
             for (int jy = 1; jy <= upcl; ++jy) {
                 const double temp1 = list_dot(&LWS(1, ipntr), &LWY(1, jpntr), indx2, 1, nenter, lane);
                 const double temp3 = list_dot(&LWS(1, ipntr), &LWY(1, jpntr), indx2, ileave, n, lane);
@@ -408,24 +462,32 @@ __device__ inline int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int 
         }
     }
     const int m2 = 2 * m;
+    #pragma unroll 1
     for (int iy = 1; iy <= col; ++iy) {
         const int is = col + iy, is1 = m + iy;
+        #pragma unroll 1
         for (int jy = 1; jy <= iy; ++jy) {
             const int js = col + jy, js1 = m + jy;
             LWN(jy, iy) = LWN1(iy, jy) / theta;
             LWN(js, is) = LWN1(is1, js1) * theta;
         }
+        #pragma unroll 1
         for (int jy = 1; jy <= iy - 1; ++jy) LWN(jy, is) = -LWN1(is1, jy);
+        #pragma unroll 1
         for (int jy = iy; jy <= col; ++jy) LWN(jy, is) = LWN1(is1, jy);
         LWN(iy, iy) += LSY(iy, iy);
     }
     if (chol_upper(w.wn, m2, col)) return -1;
     const int col2 = 2 * col;
+    #pragma unroll 1
     for (int js = col + 1; js <= col2; ++js)
         if (tri_solve_upper(w.wn, m2, col, &LWN(1, js), 1)) return -1;
+    #pragma unroll 1
     for (int is = col + 1; is <= col2; ++is)
+        #pragma unroll 1
         for (int js = is; js <= col2; ++js) {
             double dot = 0.0;
+            #pragma unroll 1
             for (int k = 1; k <= col; ++k) dot += LWN(k, is) * LWN(k, js);
             LWN(is, js) += dot;
         }
@@ -433,14 +495,18 @@ __device__ inline int ls_formk(LsWork &w, int nsub, int nenter, int ileave, int 
     return 0;
 }
 
-__device__ inline int ls_formt(LsWork &w, int col, double theta)
+__device__ __noinline__ int ls_formt(LsWork &w, int col, double theta)
 {
     const int m = kLsM;
+    #pragma unroll 1
     for (int j = 1; j <= col; ++j) LWT(1, j) = theta * LSS(1, j);
+    #pragma unroll 1
     for (int i = 2; i <= col; ++i)
+        #pragma unroll 1
         for (int j = i; j <= col; ++j) {
             const int k1 = (i < j ? i : j) - 1;
             double ddum = 0.0;
+            #pragma unroll 1
             for (int k = 1; k <= k1; ++k) ddum += LSY(i, k) * LSY(j, k) / LSY(k, k);
             LWT(i, j) = ddum + theta * LSS(i, j);
         }
@@ -448,16 +514,18 @@ __device__ inline int ls_formt(LsWork &w, int col, double theta)
 }
 
 // r = -Z'B(xcp - xk) - Z'g   (free variables, lane-striped)
-__device__ inline int ls_cmprlb(LsWork &w, const double *x, const double *g, double theta, int col,
+__device__ __noinline__ int ls_cmprlb(LsWork &w, const double *x, const double *g, double theta, int col,
                                 int head, int nfree, int lane)
 {
     const int n = w.n, m = kLsM;
     double *r = w.r, *z = w.z, *wa = w.wa;
     if (ls_bmv(w, col, wa + 2 * m, wa)) return -8;
+    #pragma unroll 1
     for (int i = 1 + lane; i <= nfree; i += SDA_WARP) {
         const int k = w.index[i - 1];
         double ri = -theta * (z[k - 1] - x[k - 1]) - g[k - 1];
         int pointr = head;
+        #pragma unroll 1
         for (int j = 1; j <= col; ++j) {
             ri += LWY(k, pointr) * wa[j - 1] + LWS(k, pointr) * (theta * wa[col + j - 1]);
             pointr = pointr % m + 1;
@@ -469,7 +537,7 @@ __device__ inline int ls_cmprlb(LsWork &w, const double *x, const double *g, dou
 }
 
 // subspace minimisation + Morales-Nocedal projection
-__device__ inline int ls_subsm(LsWork &w, int nsub, const double *l, const double *u,
+__device__ __noinline__ int ls_subsm(LsWork &w, int nsub, const double *l, const double *u,
                                const double *xx, const double *gg, double theta, int col, int head,
                                int lane)
 {
@@ -478,8 +546,10 @@ __device__ inline int ls_subsm(LsWork &w, int nsub, const double *l, const doubl
     double *x = w.z, *d = w.r, *xp = w.xp, *wv = w.wa;
     if (nsub <= 0) return 0;
     int pointr = head;
+    #pragma unroll 1
     for (int i = 1; i <= col; ++i) {
         double temp1 = 0.0, temp2 = 0.0;
+        #pragma unroll 1
         for (int j = 1 + lane; j <= nsub; j += SDA_WARP) {
             const int k = ind[j - 1];
             temp1 += LWY(k, pointr) * d[j - 1];
@@ -493,22 +563,27 @@ __device__ inline int ls_subsm(LsWork &w, int nsub, const double *l, const doubl
     }
     const int m2 = 2 * m, col2 = 2 * col;
     if (tri_solve_upper(w.wn, m2, col2, wv, 1)) return 1;
+    #pragma unroll 1
     for (int i = 0; i < col; ++i) wv[i] = -wv[i];
     if (tri_solve_upper(w.wn, m2, col2, wv, 0)) return 1;
     __syncwarp();
+    #pragma unroll 1
     for (int i = 1 + lane; i <= nsub; i += SDA_WARP) {
         const int k = ind[i - 1];
         double di = d[i - 1];
         pointr = head;
+        #pragma unroll 1
         for (int jy = 1; jy <= col; ++jy) {
             di += LWY(k, pointr) * wv[jy - 1] / theta + LWS(k, pointr) * wv[col + jy - 1];
             pointr = pointr % m + 1;
         }
         d[i - 1] = di * (1.0 / theta);
     }
+    #pragma unroll 1
     for (int i = lane; i < n; i += SDA_WARP) xp[i] = x[i];
     __syncwarp();
     int iword = 0;
+    #pragma unroll 1
     for (int i = 1 + lane; i <= nsub; i += SDA_WARP) {
         const int k = ind[i - 1];
         const double dk = d[i - 1];
@@ -522,14 +597,17 @@ __device__ inline int ls_subsm(LsWork &w, int nsub, const double *l, const doubl
     __syncwarp();
     if (iword == 0) return 0;
     double dd_p = 0.0;
+    #pragma unroll 1
     for (int i = lane; i < n; i += SDA_WARP) dd_p += (x[i] - xx[i]) * gg[i];
     dd_p = warp_sum(dd_p);
     if (dd_p > 0.0) {
+        #pragma unroll 1
         for (int i = lane; i < n; i += SDA_WARP) x[i] = xp[i];
         __syncwarp();
         // serial (order dependent) search of the first blocking bound
         double alpha = 1.0, temp1 = alpha;
         int ibd = 0;
+        #pragma unroll 1
         for (int i = 1; i <= nsub; ++i) {
             const int k = ind[i - 1];
             const double dk = d[i - 1];
@@ -551,6 +629,7 @@ __device__ inline int ls_subsm(LsWork &w, int nsub, const double *l, const doubl
             else if (dk < 0.0) { x[k - 1] = l[k - 1]; d[ibd - 1] = 0.0; }
         }
         __syncwarp();
+        #pragma unroll 1
         for (int i = 1 + lane; i <= nsub; i += SDA_WARP) {
             const int k = ind[i - 1];
             x[k - 1] += alpha * d[i - 1];
@@ -560,7 +639,7 @@ __device__ inline int ls_subsm(LsWork &w, int nsub, const double *l, const doubl
     return 0;
 }
 
-__device__ inline void ls_matupd(LsWork &w, int &itail, int iupdat, int &col, int &head,
+__device__ __noinline__ void ls_matupd(LsWork &w, int &itail, int iupdat, int &col, int &head,
                                  double &theta, double rr, double dr, double stp, double dtd,
                                  int lane)
 {
@@ -573,19 +652,25 @@ __device__ inline void ls_matupd(LsWork &w, int &itail, int iupdat, int &col, in
         itail = itail % m + 1;
         head = head % m + 1;
     }
+    #pragma unroll 1
     for (int i = 1 + lane; i <= n; i += SDA_WARP) { LWS(i, itail) = d[i - 1]; LWY(i, itail) = r[i - 1]; }
     __syncwarp();
     theta = rr / dr;
     const int c = col;
     if (iupdat > m) {
+        #pragma unroll 1
         for (int j = 1; j <= c - 1; ++j) {
+            #pragma unroll 1
             for (int i = 0; i < j; ++i) LSS(1 + i, j) = LSS(2 + i, j + 1);
+            #pragma unroll 1
             for (int i = 0; i < c - j; ++i) LSY(j + i, j) = LSY(j + 1 + i, j + 1);
         }
     }
     int pointr = head;
+    #pragma unroll 1
     for (int j = 1; j <= c - 1; ++j) {
         double a = 0.0, b = 0.0;
+        #pragma unroll 1
         for (int i = 1 + lane; i <= n; i += SDA_WARP) {
             a += d[i - 1] * LWY(i, pointr);
             b += LWS(i, pointr) * d[i - 1];
@@ -603,6 +688,7 @@ __device__ inline double ls_projgr(int n, const double *l, const double *u, cons
                                    const double *g, int lane)
 {
     double s = 0.0;
+    #pragma unroll 1
     for (int i = lane; i < n; i += SDA_WARP) {
         double gi = g[i];
         if (gi < 0.0) gi = fmax(x[i] - u[i], gi);
@@ -619,7 +705,7 @@ struct LsSearch {
 };
 enum { kLsFG = 0, kLsConv = 1, kLsWarn = 2, kLsError = 3 };
 
-__device__ inline void ls_dcstep(double &stx, double &fx, double &dx, double &sty, double &fy,
+__device__ __noinline__ void ls_dcstep(double &stx, double &fx, double &dx, double &sty, double &fy,
                                  double &dy, double &stp, double fp, double dp, int &brackt,
                                  double stpmin, double stpmax)
 {
@@ -697,7 +783,7 @@ __device__ inline void ls_dcstep(double &stx, double &fx, double &dx, double &st
     stp = stpf;
 }
 
-__device__ inline int ls_dcsrch(LsSearch &s, int start, double f, double g, double &stp,
+__device__ __noinline__ int ls_dcsrch(LsSearch &s, int start, double f, double g, double &stp,
                                 double ftol, double gtol, double xtol, double stpmin,
                                 double stpmax)
 {
@@ -754,7 +840,7 @@ __device__ inline int ls_dcsrch(LsSearch &s, int start, double f, double g, doub
 // ---- K7: f and the clipped central-difference gradient at x                        :325-345 ----
 // xe is the warp's shared-memory evaluation buffer.  Returns true when the suite monitor stopped
 // the chain (the reference would have raised out of scipy at that call).
-__device__ inline bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st, LsWork &w,
+__device__ __noinline__ bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st, LsWork &w,
                                        const double *x, double *xe, const double *lo,
                                        const double *up, double &f, double *g, int lane)
 {
@@ -772,29 +858,38 @@ __device__ inline bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st, LsWo
     }
     for (int k = lane; k < n; k += SDA_WARP) xe[k] = x[k];
     __syncwarp();
-    f = func_wrapper(a, st, xe, lane, true);
-    if (st.stop) return true;
-    for (int i = 0; i < n; ++i) {
-        const double xi = x[i];
-        double respl = kGradEps, respr = kGradEps;
-        double x1 = xi + respr;
-        if (x1 > up[i]) { x1 = up[i]; respr = x1 - xi; }
-        double x2 = xi - respl;
-        if (x2 < lo[i]) { x2 = lo[i]; respl = xi - x2; }
-        if (lane == 0) xe[i] = x1;
-        __syncwarp();
-        const double f1 = func_wrapper(a, st, xe, lane, true);
-        if (st.stop) return true;
-        __syncwarp();
-        if (lane == 0) xe[i] = x2;
-        __syncwarp();
-        const double f2 = func_wrapper(a, st, xe, lane, true);
-        if (st.stop) return true;
-        __syncwarp();
-        if (lane == 0) xe[i] = xi;
-        double gi = (f1 - f2) / (respl + respr);
+    // evaluation e = 0 is f(x); e = 2i+1 / 2i+2 are f(x + h_r e_i) / f(x - h_l e_i) -- one call
+    // site for all 1 + 2n evaluations (code size), in the reference's order (call counting)
+    double f1 = 0.0, denom = 0.0;
+    for (int e = 0; e <= 2 * n; ++e) {
+        const int i = (e - 1) >> 1;
+        const bool plus = (e & 1) != 0;
+        double xi = 0.0;
+        if (e > 0) {
+            xi = x[i];
+            double xp;
+            if (plus) {
+                double respr = kGradEps;
+                xp = xi + respr;
+                if (xp > up[i]) { xp = up[i]; respr = xp - xi; }
+                denom = respr;
+            } else {
+                double respl = kGradEps;
+                xp = xi - respl;
+                if (xp < lo[i]) { xp = lo[i]; respl = xi - xp; }
+                denom = respl + denom;                       // (respl + respr)
+            }
+            if (lane == 0) xe[i] = xp;
+            __syncwarp();
+        }
+        const double fe = func_wrapper<true>(a, st, xe, lane);
+        if (st.stop) { if (e == 0) f = fe; return true; }
+        if (e == 0) { f = fe; continue; }
+        if (plus) { f1 = fe; continue; }
+        double gi = (f1 - fe) / denom;
         if (isnan(gi) || isinf(gi)) gi = 101.0;
-        if (lane == 0) { g[i] = gi; w.gl[i] = gi; }
+        __syncwarp();
+        if (lane == 0) { xe[i] = xi; g[i] = gi; w.gl[i] = gi; }
     }
     for (int k = lane; k < n; k += SDA_WARP) w.xl[k] = x[k];
     w.fl = f;
@@ -835,7 +930,7 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
     for (;;) {
         // ---------------- generalized Cauchy point ----------------
         __syncwarp();
-        if (ls_cauchy(w, x, l, u, g, theta, col, head, sbgnrm)) {
+        if (ls_cauchy(w, x, l, u, g, theta, col, head, sbgnrm, lane)) {
             info = 0; col = 0; head = 1; theta = 1.0; iupdat = 0; updatd = 0;
             continue;
         }

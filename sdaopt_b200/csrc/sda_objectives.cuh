@@ -103,4 +103,13 @@ __device__ __forceinline__ double eval_objective(int fid, const double *x, int d
     }
 }
 
+// Out-of-line copy for the cold callers (local search, (re)initialisation): the body with all
+// registered objectives is ~4.5 K instructions, and inlining it at every call site grew the
+// L-BFGS-B code to 750 KB -- ncu showed 85 % of its cycles stalled on instruction fetch.
+__device__ __noinline__ double eval_objective_ool(int fid, const double *x, int dim,
+                                                  const double *params, int lane)
+{
+    return eval_objective(fid, x, dim, params, lane);
+}
+
 }  // namespace sda
