@@ -1,9 +1,10 @@
-// sda_chain.cuh -- one annealing chain on one warp: K2 (visit) + K3 (objective) + K4 (accept and
-// bookkeeping) + K5 (local-search policy) + K8 (re-anneal) + K9 (suite monitor), fused.
+// sda_chain.cuh -- one annealing chain on one chain group (G lanes): K2 (visit) + K3 (objective) +
+// K4 (accept and bookkeeping) + K8 (re-anneal) + K9 (suite monitor), fused.
 //
-// Restates SDARunner.search (_sda.py:393-418), MarkovChain.run (:192-234),
-// MarkovChain.local_search (:236-273), EnergyState.reset (:135-166) and the suite wrapper
-// Algo._funcwrapped (benchmark/bench.py:292-321) for a warp.  All scalars are warp-uniform.
+// Restates MarkovChain.run (_sda.py:192-234), EnergyState.reset (:135-166) and the suite wrapper
+// Algo._funcwrapped (benchmark/bench.py:292-321) for a group.  Scalars are group-uniform (every
+// lane of the group holds the same value); vectors live in the group's shared-memory rows,
+// coordinate k owned by lane k mod G.  All barriers are group-masked (sda_device.cuh).
 #pragma once
 
 #include "sda_device.cuh"
@@ -39,6 +40,7 @@ struct DeviceArgs {
     long long ls_stride;            // doubles per warp slot
     unsigned long long *work_counter;
     int ls_maxiter;                 // clamp(6*dim, 100, 1000)  _sda.py:291-296
+    int group;                      // lanes per chain (power of two <= 32)
 };
 
 // the search box in shared memory: lower, upper, upper - lower and 1 / (upper - lower)
@@ -59,10 +61,11 @@ struct ChainState {
 // the callable handed to sda(): objective + suite monitor (bench.py:292-321)
 template <bool INLINE_EVAL>
 __device__ __forceinline__ double call_func(const DeviceArgs &a, ChainState &st, const double *x,
-                                            int lane)
+                                            const Group &g)
 {
-    const double res = INLINE_EVAL ? eval_objective(a.functor, x, a.dim, a.params, lane)
-                                   : eval_objective_ool(a.functor, x, a.dim, a.params, lane);
+    const double res = INLINE_EVAL ? eval_objective(a.functor, x, a.dim, a.params, g)
+                                   : eval_objective_ool(a.functor, x, a.dim, a.params, g.G,
+                                                        g.gid * g.G + g.gl);
     if (a.max_calls > 0 && !st.stop) {
         st.mon_calls += 1;                              // bench.py:300
         if (st.mon_calls >= a.max_calls) {              // bench.py:301-304
@@ -80,16 +83,16 @@ __device__ __forceinline__ double call_func(const DeviceArgs &a, ChainState &st,
 // ObjectiveFunWrapper.func_wrapper                                                :321-323
 template <bool IN_LS>
 __device__ __forceinline__ double func_wrapper(const DeviceArgs &a, ChainState &st,
-                                               const double *x, int lane)
+                                               const double *x, const Group &g)
 {
     st.ncall += 1;
     if (IN_LS) st.ncall_ls += 1;
-    return call_func<!IN_LS>(a, st, x, lane);
+    return call_func<!IN_LS>(a, st, x, g);
 }
 
-__device__ __forceinline__ void copy_vec(double *dst, const double *src, int dim, int lane)
+__device__ __forceinline__ void copy_vec(double *dst, const double *src, int dim, const Group &g)
 {
-    for (int k = lane; k < dim; k += SDA_WARP) dst[k] = src[k];
+    for (int k = g.gl; k < dim; k += g.G) dst[k] = src[k];
 }
 
 template <bool TAPE>
@@ -101,49 +104,50 @@ struct Rng<false> { PhiloxRng p; };
 
 // lower + random_sample(D) * (upper - lower)                                      :137-138, :157-158
 template <bool TAPE>
-__device__ __forceinline__ void draw_location(Rng<TAPE> &rng, double *x_cur, const double *lo,
-                                              const double *up, int dim, uint32_t attempt, int lane)
+__device__ __forceinline__ void draw_location(Rng<TAPE> &rng, double *x_cur, const Box &bx, int dim,
+                                              uint32_t attempt, const Group &g)
 {
     if constexpr (TAPE) {
         for (int k = 0; k < dim; ++k) {
             const double u = rng.t.next();
-            if ((k & 31) == lane) x_cur[k] = __dadd_rn(lo[k], __dmul_rn(u, __dsub_rn(up[k], lo[k])));
+            if ((k & (g.G - 1)) == g.gl)
+                x_cur[k] = __dadd_rn(bx.lo[k], __dmul_rn(u, __dsub_rn(bx.up[k], bx.lo[k])));
         }
     } else {
-        for (int k = lane; k < dim; k += SDA_WARP) {
+        for (int k = g.gl; k < dim; k += g.G) {
             double u, u2;
             rng.p.pair(kInit, (uint32_t)k, attempt, u, u2);
-            x_cur[k] = __dadd_rn(lo[k], __dmul_rn(u, __dsub_rn(up[k], lo[k])));
+            x_cur[k] = __dadd_rn(bx.lo[k], __dmul_rn(u, __dsub_rn(bx.up[k], bx.lo[k])));
         }
     }
-    __syncwarp();
+    group_sync(g);
 }
 
 // EnergyState.reset                                                               :135-166
 template <bool TAPE>
 __device__ __noinline__ int energy_reset(const DeviceArgs &a, ChainState &st, Rng<TAPE> &rng,
-                                            double *x_cur, const double *lo, const double *up,
-                                            const double *x0, double *xbest, int lane)
+                                         double *x_cur, const Box &bx, const double *x0,
+                                         double *xbest, const Group &g)
 {
     const int dim = a.dim;
     uint32_t attempt = 0;
-    if (x0 == nullptr) draw_location<TAPE>(rng, x_cur, lo, up, dim, attempt++, lane);
-    else { copy_vec(x_cur, x0, dim, lane); __syncwarp(); }
+    if (x0 == nullptr) draw_location<TAPE>(rng, x_cur, bx, dim, attempt++, g);
+    else { copy_vec(x_cur, x0, dim, g); group_sync(g); }
     int reinit = 0;
     for (;;) {
         bool done = false;
-        st.e_cur = call_func<false>(a, st, x_cur, lane); // owf.func: not counted      :144
+        st.e_cur = call_func<false>(a, st, x_cur, g);   // owf.func: not counted      :144
         if (st.stop) return 0;
         if (st.e_cur >= kBigValue || isnan(st.e_cur)) {
             if (reinit >= kMaxReinit) return SDA_CHAIN_REINIT_FAILED;
-            draw_location<TAPE>(rng, x_cur, lo, up, dim, attempt++, lane);
+            draw_location<TAPE>(rng, x_cur, bx, dim, attempt++, g);
             reinit += 1;
         } else {
             done = true;
         }
         if (!st.have_best) {                            // :163-165
             st.ebest = st.e_cur;
-            copy_vec(xbest, x_cur, dim, lane);
+            copy_vec(xbest, x_cur, dim, g);
             st.have_best = 1;
         }
         if (done) break;
@@ -152,9 +156,9 @@ __device__ __noinline__ int energy_reset(const DeviceArgs &a, ChainState &st, Rn
 }
 
 __device__ __forceinline__ void trace(const DeviceArgs &a, ChainState &st, long long chain,
-                                      double e, int dec, int lane)
+                                      double e, int dec, const Group &g)
 {
-    if (a.out.trace_e != nullptr && st.trace_pos < a.trace_len && lane == 0) {
+    if (a.out.trace_e != nullptr && st.trace_pos < a.trace_len && g.gl == 0) {
         a.out.trace_e[chain * a.trace_len + st.trace_pos] = e;
         a.out.trace_d[chain * a.trace_len + st.trace_pos] = (uint8_t)dec;
     }
@@ -166,23 +170,23 @@ __device__ __forceinline__ void trace(const DeviceArgs &a, ChainState &st, long 
 __device__ __forceinline__ void accept_step(const DeviceArgs &a, ChainState &st, long long chain,
                                             double e, double r, double t_step, long long j,
                                             int single, double *x_cur, double *x_vis,
-                                            double *xbest, double *xmin, int lane)
+                                            double *xbest, double *xmin, const Group &g)
 {
     const int dim = a.dim;
     if (e < st.e_cur) {
         int dec = SDA_DEC_IMPROVE;
         st.e_cur = e;
-        if (single >= 0) { if (lane == 0) x_cur[single] = x_vis[single]; }
-        else copy_vec(x_cur, x_vis, dim, lane);
+        if (single >= 0) { if (g.gl == 0) x_cur[single] = x_vis[single]; }
+        else copy_vec(x_cur, x_vis, dim, g);
         if (e < st.ebest) {
             st.ebest = e;
-            copy_vec(xbest, x_vis, dim, lane);
+            copy_vec(xbest, x_vis, dim, g);
             st.state_improved = 1;
             st.not_improved_idx = 0;
             dec = SDA_DEC_NEW_BEST;
         }
-        __syncwarp();
-        trace(a, st, chain, e, dec, lane);
+        group_sync(g);
+        trace(a, st, chain, e, dec, g);
     } else {
         int dec = SDA_DEC_REJECT;
         const double pqa_temp =
@@ -192,22 +196,22 @@ __device__ __forceinline__ void accept_step(const DeviceArgs &a, ChainState &st,
         else pqa = exp(__ddiv_rn(log(pqa_temp), 1. - a.qa));
         if (r <= pqa) {
             st.e_cur = e;
-            if (single >= 0) { if (lane == 0) x_cur[single] = x_vis[single]; }
-            else copy_vec(x_cur, x_vis, dim, lane);
-            __syncwarp();
-            copy_vec(xmin, x_cur, dim, lane);           // self.xmin = np.copy(current_location)
+            if (single >= 0) { if (g.gl == 0) x_cur[single] = x_vis[single]; }
+            else copy_vec(x_cur, x_vis, dim, g);
+            group_sync(g);
+            copy_vec(xmin, x_cur, dim, g);              // self.xmin = np.copy(current_location)
             dec = SDA_DEC_METRO_ACCEPT;
         } else if (single >= 0) {
-            if (lane == 0) x_vis[single] = x_cur[single];   // undo the one-coordinate proposal
-            __syncwarp();
+            if (g.gl == 0) x_vis[single] = x_cur[single];   // undo the one-coordinate proposal
+            group_sync(g);
         }
         if (st.not_improved_idx >= st.not_improved_max_idx) {
             if (j == 0 || st.e_cur < st.emin) {
                 st.emin = st.e_cur;
-                copy_vec(xmin, x_cur, dim, lane);
+                copy_vec(xmin, x_cur, dim, g);
             }
         }
-        trace(a, st, chain, e, dec, lane);
+        trace(a, st, chain, e, dec, g);
     }
 }
 
@@ -216,9 +220,11 @@ template <bool TAPE>
 __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, Rng<TAPE> &rng,
                                            long long chain, long long step, double temperature,
                                            double sigmax, double *x_cur, double *x_vis, double *sv,
-                                           const Box &bx, double *xbest, double *xmin, int lane)
+                                           const Box &bx, double *xbest, double *xmin,
+                                           const Group &g)
 {
     const int dim = a.dim;
+    const int G = g.G;
     const double t_step = __ddiv_rn(temperature, (double)(step + 1));
     const VisitConst vc = { sigmax, a.qv - 1.0, 3.0 - a.qv };
     st.not_improved_idx += 1;
@@ -231,12 +237,12 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
             if constexpr (TAPE) {
                 for (int k = 0; k < dim; ++k) {
                     const double v = visit_sample_tape(rng.t, vc);
-                    if ((k & 31) == lane) sv[k] = v;
+                    if ((k & (G - 1)) == g.gl) sv[k] = v;
                 }
                 const double upper_sample = rng.t.next();
                 const double lower_sample = rng.t.next();
-                __syncwarp();
-                for (int k = lane; k < dim; k += SDA_WARP) {
+                group_sync(g);
+                for (int k = g.gl; k < dim; k += G) {
                     double v = sv[k];
                     if (v > kTailLimit) v = __dmul_rn(kTailLimit, upper_sample);
                     else if (v < -kTailLimit) v = __dmul_rn(-kTailLimit, lower_sample);
@@ -244,18 +250,24 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                 }
             } else {
                 rng.p.j = (uint32_t)j;
-                double upper_sample, lower_sample;
-                rng.p.pair(kClip, 0, 0, upper_sample, lower_sample);
+                // the two clip uniforms are "always drawn" in the reference (:46-47); with a
+                // counter-based stream drawing is addressing, so they are computed lazily
+                bool have_clip = false;
+                double upper_sample = 0.0, lower_sample = 0.0;
                 // two coordinates per lane and trip: the two log/sqrt/exp/div chains are
-                // independent, which doubles the ILP of the FP64 pipe at 4 warps per SMSP
-                for (int k0 = lane; k0 < dim; k0 += 2 * SDA_WARP) {
-                    const int k1 = k0 + SDA_WARP;
+                // independent, which doubles the ILP of the FP64 pipe
+                for (int k0 = g.gl; k0 < dim; k0 += 2 * G) {
+                    const int k1 = k0 + G;
                     const bool two = k1 < dim;
                     double xg0, yg0, s0, xg1 = 0.5, yg1 = 0.5, s1 = 0.5;
                     polar_pair_philox(rng.p, (uint32_t)k0, xg0, yg0, s0);
                     if (two) polar_pair_philox(rng.p, (uint32_t)k1, xg1, yg1, s1);
                     double v0 = visit_from_polar(xg0, yg0, s0, vc);
                     double v1 = visit_from_polar(xg1, yg1, s1, vc);
+                    if (!have_clip && (fabs(v0) > kTailLimit || (two && fabs(v1) > kTailLimit))) {
+                        rng.p.pair(kClip, 0, 0, upper_sample, lower_sample);
+                        have_clip = true;
+                    }
                     if (v0 > kTailLimit) v0 = __dmul_rn(kTailLimit, upper_sample);
                     else if (v0 < -kTailLimit) v0 = __dmul_rn(-kTailLimit, lower_sample);
                     if (v1 > kTailLimit) v1 = __dmul_rn(kTailLimit, upper_sample);
@@ -265,15 +277,15 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                         x_vis[k1] = wrap_coord(__dadd_rn(v1, x_cur[k1]), bx.lo[k1], bx.range[k1], bx.inv_range[k1]);
                 }
             }
-            __syncwarp();
+            group_sync(g);
         } else {
             const int index = (int)(j - dim);
             if (j == dim) {
                 // entering the one-coordinate phase: x_vis := x_cur, and (Philox) draw the D
                 // state-independent one-coordinate jumps of this step in parallel
-                copy_vec(x_vis, x_cur, dim, lane);
+                copy_vec(x_vis, x_cur, dim, g);
                 if constexpr (!TAPE) {
-                    for (int k = lane; k < dim; k += SDA_WARP) {
+                    for (int k = g.gl; k < dim; k += G) {
                         rng.p.j = (uint32_t)(dim + k);
                         double v = visit_sample_philox(rng.p, (uint32_t)k, vc);
                         if (v > kTailLimit || v < -kTailLimit) {
@@ -284,7 +296,7 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                         sv[k] = v;
                     }
                 }
-                __syncwarp();
+                group_sync(g);
             }
             double visit;
             if constexpr (TAPE) {
@@ -295,15 +307,15 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                 rng.p.j = (uint32_t)j;
                 visit = sv[index];
             }
-            if (lane == 0)
+            if (g.gl == 0)
                 x_vis[index] = wrap_coord(__dadd_rn(visit, x_cur[index]), bx.lo[index],
                                           bx.range[index], bx.inv_range[index]);
-            __syncwarp();
+            group_sync(g);
             single = index;
         }
         if constexpr (TAPE) { if (rng.t.exhausted) return; }
         // ---- K3: objective                                                      :203
-        const double e = func_wrapper<false>(a, st, x_vis, lane);
+        const double e = func_wrapper<false>(a, st, x_vis, g);
         if (st.stop) return;
         // ---- K4: acceptance.  The uniform is drawn only when e >= E_cur          :216
         double r = 0.0;
@@ -311,7 +323,7 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
             if constexpr (TAPE) { r = rng.t.next(); if (rng.t.exhausted) return; }
             else { double r2; rng.p.pair(kAccept, 0, 0, r, r2); }
         }
-        accept_step(a, st, chain, e, r, t_step, j, single, x_cur, x_vis, xbest, xmin, lane);
+        accept_step(a, st, chain, e, r, t_step, j, single, x_cur, x_vis, xbest, xmin, g);
     }
 }
 

@@ -64,6 +64,43 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Chain groups.  A chain is advanced by G consecutive lanes (G = 1, 2, 4, ... 32, chosen from the
+// dimension so that ceil(D/G)*G wastes few lanes); a warp carries 32/G chains side by side.  All
+// synchronisation inside group code uses the group's lane mask, so groups of one warp may diverge
+// (local search, re-initialisation, early exit) without deadlock; the warp-level loop re-aligns
+// them with full-mask barriers between phases so that they share instruction issue.
+// ---------------------------------------------------------------------------------------------
+struct Group {
+    int G;          // lanes per chain
+    int gl;         // lane index inside the group: owns coordinates gl, gl + G, ...
+    int gid;        // group index inside the warp
+    unsigned mask;  // lanes of this group
+};
+
+__device__ __forceinline__ Group make_group(int G, int lane)
+{
+    Group g;
+    g.G = G;
+    g.gl = lane & (G - 1);
+    g.gid = lane / G;
+    g.mask = (G == 32) ? SDA_FULL_MASK : (((1u << G) - 1u) << (g.gid * G));
+    return g;
+}
+
+// reductions over the lanes of a group (xor butterfly: every lane ends with identical bits)
+__device__ __forceinline__ double group_sum(double v, const Group &g)
+{
+    for (int o = g.G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+    return v;
+}
+__device__ __forceinline__ double group_prod(double v, const Group &g)
+{
+    for (int o = g.G >> 1; o > 0; o >>= 1) v *= __shfl_xor_sync(g.mask, v, o);
+    return v;
+}
+__device__ __forceinline__ void group_sync(const Group &g) { __syncwarp(g.mask); }
+
+// ---------------------------------------------------------------------------------------------
 // warp reductions: every lane receives bit-identical results
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v)

@@ -18,156 +18,81 @@
 
 namespace sda {
 
-// MarkovChain.local_search                                                        :236-273
+#ifndef SDA_ANNEAL_MIN_BLOCKS
+#define SDA_ANNEAL_MIN_BLOCKS 2
+#endif
+
+// what a chain group does next (per-group state machine of the persistent kernel)
+enum Pending : int { kNone = 0, kDoInit = 10, kReanneal = 11, kStep = 12 };
+// local-search request of a group, served by the whole warp
+enum LsReq : int { kLsNone = 0, kLsFromBest = 1, kLsFromMin = 2 };
+
+__device__ __forceinline__ long long shfl_ll(long long v, int src)
+{
+    return __shfl_sync(SDA_FULL_MASK, v, src);
+}
+
+// make the chain state of the group led by lane `src` warp-uniform (for the warp-wide L-BFGS-B)
+__device__ __forceinline__ ChainState bcast_state(const ChainState &s, int src)
+{
+    ChainState t;
+    t.e_cur = __shfl_sync(SDA_FULL_MASK, s.e_cur, src);
+    t.ebest = __shfl_sync(SDA_FULL_MASK, s.ebest, src);
+    t.emin = __shfl_sync(SDA_FULL_MASK, s.emin, src);
+    t.not_improved_idx = shfl_ll(s.not_improved_idx, src);
+    t.not_improved_max_idx = shfl_ll(s.not_improved_max_idx, src);
+    t.ncall = shfl_ll(s.ncall, src);
+    t.ncall_ls = shfl_ll(s.ncall_ls, src);
+    t.n_ls = shfl_ll(s.n_ls, src);
+    t.mon_calls = shfl_ll(s.mon_calls, src);
+    t.ncall_hit = shfl_ll(s.ncall_hit, src);
+    t.f_hit = __shfl_sync(SDA_FULL_MASK, s.f_hit, src);
+    t.trace_pos = shfl_ll(s.trace_pos, src);
+    t.state_improved = __shfl_sync(SDA_FULL_MASK, s.state_improved, src);
+    t.stop = __shfl_sync(SDA_FULL_MASK, s.stop, src);
+    t.hit = __shfl_sync(SDA_FULL_MASK, s.hit, src);
+    t.status = __shfl_sync(SDA_FULL_MASK, s.status, src);
+    t.have_best = __shfl_sync(SDA_FULL_MASK, s.have_best, src);
+    return t;
+}
+
 // The chain state and the L-BFGS-B work descriptor are handed to the (noinline) minimiser as
 // copies so that the annealing loop's own state never has its address taken and stays in registers.
 __device__ __forceinline__ int call_local_search(const DeviceArgs &a, ChainState &st, double *ls_slot,
-                                                 double *ls_smem, const double *x_start, double *xe, const double *lo,
-                                                 const double *up, double &e, double *&x_out, int lane)
+                                                 double *ls_smem, const double *x_start, double *xe,
+                                                 const double *lo, const double *up, double &e,
+                                                 int lane)
 {
     ChainState tmp = st;
     LsWork w;
     w.bind(ls_slot, ls_smem, a.dim);
     const int ok = ofw_local_search(a, tmp, w, x_start, xe, lo, up, e, lane);
     st = tmp;
-    x_out = w.x;
     return ok;
-}
-
-__device__ inline void markov_local_search(const DeviceArgs &a, ChainState &st, double *ls_slot,
-                                           double *ls_smem, double *x_cur, double *x_vis, const double *lo,
-                                           const double *up, double *xbest, double *xmin, int lane)
-{
-    const int dim = a.dim;
-    double e;
-    double *wx = nullptr;
-    if (st.state_improved) {
-        call_local_search(a, st, ls_slot, ls_smem, xbest, x_vis, lo, up, e, wx, lane);
-        if (st.stop) return;
-        if (e < st.ebest) {
-            st.not_improved_idx = 0;
-            st.ebest = e;
-            copy_vec(xbest, wx, dim, lane);
-            st.e_cur = e;
-            copy_vec(x_cur, wx, dim, lane);
-            __syncwarp();
-            return;
-        }
-    }
-    // :254-258 is dead code in the reference (K = 100*D is never < 90*D): no uniform is drawn
-    if (st.not_improved_idx >= st.not_improved_max_idx) {
-        const int ok = call_local_search(a, st, ls_slot, ls_smem, xmin, x_vis, lo, up, e, wx, lane);
-        if (st.stop) return;
-        if (ok) copy_vec(xmin, wx, dim, lane);
-        st.emin = e;
-        st.not_improved_idx = 0;
-        st.not_improved_max_idx = dim;
-        if (e < st.ebest) {
-            st.ebest = st.emin;
-            copy_vec(xbest, wx, dim, lane);
-            st.e_cur = e;
-            copy_vec(x_cur, wx, dim, lane);
-        }
-        __syncwarp();
-    }
 }
 
 template <bool TAPE>
 __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState &st, Rng<TAPE> &rng,
-                                                 double *x_cur, const double *lo, const double *up,
-                                                 const double *x0, double *xbest, int lane)
+                                                 double *x_cur, const Box &bx, const double *x0,
+                                                 double *xbest, const Group &g)
 {
     ChainState tmp = st;
     Rng<TAPE> r2 = rng;
-    const int err = energy_reset<TAPE>(a, tmp, r2, x_cur, lo, up, x0, xbest, lane);
+    const int err = energy_reset<TAPE>(a, tmp, r2, x_cur, bx, x0, xbest, g);
     st = tmp;
     rng = r2;
     return err;
 }
 
-// SDARunner.__init__ + search + result for one chain                               :357-428
-template <bool TAPE>
-__device__ inline void run_chain(const DeviceArgs &a, long long chain, double *x_cur, double *x_vis,
-                                 double *sv, const Box &bx, double *ls_slot, double *ls_smem, int lane)
-{
-    const int dim = a.dim;
-    const double *lo = bx.lo, *up = bx.up;
-    ChainState st;
-    st.e_cur = st.ebest = st.emin = 0.0;
-    st.not_improved_idx = 0; st.not_improved_max_idx = 1000;     // :186-187
-    st.ncall = st.ncall_ls = st.n_ls = 0;
-    st.mon_calls = 0; st.ncall_hit = a.max_calls;                // bench.py:269
-    st.f_hit = __longlong_as_double(0x7ff0000000000000LL);       // bench.py:272
-    st.trace_pos = 0;
-    st.state_improved = 0; st.stop = 0; st.hit = 0; st.status = 0; st.have_best = 0;
-
-    Rng<TAPE> rng;
-    if constexpr (TAPE) {
-        rng.t.tape = a.tape + chain * a.tape_len;
-        rng.t.pos = 0; rng.t.len = a.tape_len; rng.t.exhausted = false;
-    } else {
-        const unsigned long long s = a.seeds ? a.seeds[chain] : (unsigned long long)chain;
-        rng.p.ph.k0 = (uint32_t)s; rng.p.ph.k1 = (uint32_t)(s >> 32);
-        rng.p.iter = 0; rng.p.j = 0xFFFFFFu;
-    }
-    double *xbest = a.out.x + chain * dim;
-    double *xmin = a.xmin + chain * dim;
-
-    int err = call_energy_reset<TAPE>(a, st, rng, x_cur, lo, up,
-                                      a.x0 ? a.x0 + chain * dim : nullptr, xbest, lane);
-    long long iter = 0;
-    if (!err && !st.stop) {
-        st.emin = st.e_cur;                                      // :176-177
-        copy_vec(xmin, x_cur, dim, lane);
-        bool max_steps_reached = false;
-        while (!max_steps_reached && !st.stop && !err) {
-            if constexpr (TAPE) { if (rng.t.exhausted) break; }
-            for (long long i = 0; i < a.maxiter; ++i) {
-                double temperature, sigmax;
-                if (i < a.table_len) { temperature = a.temp_table[i]; sigmax = a.sigmax_table[i]; }
-                else { temperature = a.temp_table[a.table_len - 1]; sigmax = a.sigmax_table[a.table_len - 1]; }
-                iter += 1;
-                if constexpr (!TAPE) { rng.p.iter = (uint32_t)iter; rng.p.j = 0xFFFFFFu; }
-                if (iter == a.maxiter) { max_steps_reached = true; break; }          // :404-406
-                if (temperature < a.temperature_restart) {                             // :408-410
-                    err = call_energy_reset<TAPE>(a, st, rng, x_cur, lo, up, nullptr, xbest, lane);
-                    break;
-                }
-                markov_run<TAPE>(a, st, rng, chain, i, temperature, sigmax, x_cur, x_vis, sv, bx,
-                                 xbest, xmin, lane);                                   // :412
-                if (st.stop) break;
-                if constexpr (TAPE) { if (rng.t.exhausted) break; }
-                if ((double)st.ncall >= a.maxfun) break;                               // :413-414
-                if (!a.pure_sa) {                                                      // :415-418
-                    markov_local_search(a, st, ls_slot, ls_smem, x_cur, x_vis, lo, up, xbest, xmin, lane);
-                    if (st.stop) break;
-                    if ((double)st.ncall >= a.maxfun) break;
-                }
-            }
-            if (a.maxiter <= 0) break;
-        }
-    }
-    if constexpr (TAPE) { if (rng.t.exhausted) err |= SDA_CHAIN_TAPE_EXHAUSTED; }
-    __syncwarp();
-    if (lane == 0) {
-        a.out.fun[chain] = st.ebest;
-        a.out.nit[chain] = iter;
-        a.out.ncall[chain] = st.ncall;
-        a.out.status[chain] = err;
-        if (a.out.ncall_ls) a.out.ncall_ls[chain] = st.ncall_ls;
-        if (a.out.n_ls) a.out.n_ls[chain] = st.n_ls;
-        if (a.out.hit) a.out.hit[chain] = st.hit;
-        if (a.out.ncall_hit) a.out.ncall_hit[chain] = st.ncall_hit;
-        if (a.out.f_hit) a.out.f_hit[chain] = st.f_hit;
-        if constexpr (TAPE) { if (a.out.tape_used) a.out.tape_used[chain] = rng.t.pos; }
-        else { if (a.out.tape_used) a.out.tape_used[chain] = 0; }
-    }
-}
-
-// shared memory: lower[D] upper[D] range[D] 1/range[D] | per warp: x_cur[D] x_vis[D] sv[D]
-#ifndef SDA_ANNEAL_MIN_BLOCKS
-#define SDA_ANNEAL_MIN_BLOCKS 2
-#endif
+// shared memory: lower[D] upper[D] range[D] 1/range[D]
+//              | per warp: 32/G chains x { x_cur[D] x_vis[D] sv[D] } | per warp: L-BFGS-B matrices
+//
+// Persistent kernel.  Every chain group runs the state machine of SDARunner.search (_sda.py:393-418)
+// for one chain at a time: INIT -> { STEP | REANNEAL }* -> finished -> pull the next chain from the
+// device counter.  One pass of the warp loop = at most one (re)initialisation, one Markov step
+// (MarkovChain.run, 2*D evaluations) and the local searches that step triggers, for every group of
+// the warp; full-mask barriers between the phases keep the groups aligned so that 32/G chains
+// share every issued instruction, whatever step, chain or function-call count each one is at.
 template <bool TAPE>
 __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(const DeviceArgs a)
 {
@@ -176,6 +101,9 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
+    const int G = a.group;
+    const int NG = SDA_WARP / G;
+    const Group g = make_group(G, lane);
     double *lo = smem;
     double *up = smem + dim;
     double *rg = smem + 2 * dim;
@@ -188,33 +116,207 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
     }
     __syncthreads();
     const Box bx = { lo, up, rg, irg };
-    double *x_cur = smem + 4 * dim + (size_t)warp * 3 * dim;
+    double *warp_rows = smem + 4 * dim + (size_t)warp * NG * 3 * dim;
+    double *x_cur = warp_rows + (size_t)g.gid * 3 * dim;
     double *x_vis = x_cur + dim;
     double *sv = x_vis + dim;
     const long long slot = (long long)blockIdx.x * warps_per_block + warp;
     double *ls_slot = a.ls_work ? a.ls_work + slot * a.ls_stride : nullptr;
-    // per-warp shared-memory block of the L-BFGS-B middle matrices (only with local search on)
-    double *ls_smem = smem + 4 * dim + (size_t)warps_per_block * 3 * dim + (size_t)warp * ls_smem_doubles();
+    double *ls_smem = smem + 4 * dim + (size_t)warps_per_block * NG * 3 * dim +
+                      (size_t)warp * ls_smem_doubles();
+
+    // ---- per-group state -------------------------------------------------------------------
+    ChainState st;
+    Rng<TAPE> rng;
+    long long chain = -1, iter = 0, step_i = 0;
+    int pending = kNone, err = 0;
+    bool have = false, queue_empty = false;
+    double *xbest = nullptr, *xmin = nullptr;
+
     for (;;) {
-        unsigned long long c = 0;
-        if (lane == 0) c = atomicAdd(a.work_counter, 1ULL);
-        c = __shfl_sync(SDA_FULL_MASK, c, 0);
-        if ((long long)c >= a.n_chains) break;
-        run_chain<TAPE>(a, (long long)c, x_cur, x_vis, sv, bx, ls_slot, ls_smem, lane);
+        // ---- phase 0: idle groups pull the next chain -------------------------------------------
+        if (!have && !queue_empty) {
+            unsigned long long c = 0;
+            if (g.gl == 0) c = atomicAdd(a.work_counter, 1ULL);
+            c = __shfl_sync(g.mask, c, 0, G);
+            if ((long long)c < a.n_chains) {
+                chain = (long long)c;
+                have = true;
+                st.e_cur = st.ebest = st.emin = 0.0;
+                st.not_improved_idx = 0; st.not_improved_max_idx = 1000;     // :186-187
+                st.ncall = st.ncall_ls = st.n_ls = 0;
+                st.mon_calls = 0; st.ncall_hit = a.max_calls;                // bench.py:269
+                st.f_hit = __longlong_as_double(0x7ff0000000000000LL);       // bench.py:272
+                st.trace_pos = 0;
+                st.state_improved = 0; st.stop = 0; st.hit = 0; st.status = 0; st.have_best = 0;
+                if constexpr (TAPE) {
+                    rng.t.tape = a.tape + chain * a.tape_len;
+                    rng.t.pos = 0; rng.t.len = a.tape_len; rng.t.exhausted = false;
+                } else {
+                    const unsigned long long s = a.seeds ? a.seeds[chain] : (unsigned long long)chain;
+                    rng.p.ph.k0 = (uint32_t)s; rng.p.ph.k1 = (uint32_t)(s >> 32);
+                    rng.p.iter = 0; rng.p.j = 0xFFFFFFu;
+                }
+                xbest = a.out.x + chain * dim;
+                xmin = a.xmin + chain * dim;
+                iter = 0; step_i = 0; err = 0;
+                pending = kDoInit;
+            } else {
+                queue_empty = true;
+            }
+        }
+        if (!__any_sync(SDA_FULL_MASK, have)) break;
+
+        // ---- phase 1: SDARunner.__init__ :375-376 / re-anneal :408-410 ----------------------------
+        if (have && (pending == kDoInit || pending == kReanneal)) {
+            const double *x0 = (pending == kDoInit && a.x0) ? a.x0 + chain * dim : nullptr;
+            err = call_energy_reset<TAPE>(a, st, rng, x_cur, bx, x0, xbest, g);
+            if (pending == kDoInit && !err && !st.stop) {
+                st.emin = st.e_cur;                                      // :176-177
+                copy_vec(xmin, x_cur, dim, g);
+            }
+            pending = kStep;
+        }
+        __syncwarp();
+
+        // ---- phase 2: the loop header of SDARunner.search :397-410 -------------------------------
+        bool do_step = false, finished = false;
+        double temperature = 0.0, sigmax = 0.0;
+        if (have) {
+            bool tape_out = false;
+            if constexpr (TAPE) tape_out = rng.t.exhausted;
+            if (err || st.stop || tape_out || a.maxiter <= 0) {
+                finished = true;
+            } else {
+                const long long ti = step_i < a.table_len ? step_i : a.table_len - 1;
+                temperature = a.temp_table[ti];
+                sigmax = a.sigmax_table[ti];
+                iter += 1;
+                if constexpr (!TAPE) { rng.p.iter = (uint32_t)iter; rng.p.j = 0xFFFFFFu; }
+                if (iter == a.maxiter) finished = true;                                // :404-406
+                else if (temperature < a.temperature_restart) { pending = kReanneal; step_i = 0; } // :408-410
+                else do_step = true;
+            }
+        }
+
+        // ---- phase 3: MarkovChain.run :412 ---------------------------------------------------------
+        if (do_step)
+            markov_run<TAPE>(a, st, rng, chain, step_i, temperature, sigmax, x_cur, x_vis, sv, bx,
+                             xbest, xmin, g);
+        __syncwarp();
+
+        // ---- phase 4: after the step :413-418, and the local-search policy :236-273 -----------------
+        int ls_req = kLsNone;
+        if (do_step) {
+            bool tape_out = false;
+            if constexpr (TAPE) tape_out = rng.t.exhausted;
+            if (st.stop || tape_out) {
+                finished = true;
+            } else if ((double)st.ncall >= a.maxfun) {
+                step_i = 0;                                 // `break`: the while loop restarts at i = 0
+            } else if (!a.pure_sa) {
+                if (st.state_improved) ls_req = kLsFromBest;                                   // :241
+                else if (st.not_improved_idx >= st.not_improved_max_idx) ls_req = kLsFromMin;  // :261
+                step_i += 1;
+            } else {
+                step_i += 1;
+            }
+        }
+        // two serving rounds: a search from xbest that does not improve may be followed by the
+        // stagnation search from xmin (:251-273)
+        for (int round = 0; round < 2; ++round) {
+            if (!__any_sync(SDA_FULL_MASK, ls_req != kLsNone)) break;
+            for (int gi = 0; gi < NG; ++gi) {
+                const int src = gi * G;
+                const int req = __shfl_sync(SDA_FULL_MASK, ls_req, src);
+                if (req == kLsNone) continue;
+                // the whole warp minimises for group gi: warp-uniform copies of its state
+                ChainState ts = bcast_state(st, src);
+                const long long tchain = shfl_ll(chain, src);
+                double *t_xbest = a.out.x + tchain * dim;
+                double *t_xmin = a.xmin + tchain * dim;
+                double *t_xe = warp_rows + (size_t)gi * 3 * dim + dim;   // that group's x_vis row
+                double e;
+                const int ok = call_local_search(a, ts, ls_slot, ls_smem,
+                                                 req == kLsFromBest ? t_xbest : t_xmin, t_xe, lo, up,
+                                                 e, lane);
+                const double *wx = ls_slot + 2LL * kLsM * dim + 6LL * dim;   // LsWork::x
+                if (g.gid == gi) {
+                    // counters and monitor state come back from the warp-uniform copy
+                    st.ncall = ts.ncall; st.ncall_ls = ts.ncall_ls; st.n_ls = ts.n_ls;
+                    st.mon_calls = ts.mon_calls; st.ncall_hit = ts.ncall_hit; st.f_hit = ts.f_hit;
+                    st.hit = ts.hit; st.stop = ts.stop;
+                    if (st.stop) {
+                        ls_req = kLsNone;
+                        finished = true;
+                    } else if (req == kLsFromBest) {
+                        ls_req = kLsNone;
+                        if (e < st.ebest) {                                          // :244-250
+                            st.not_improved_idx = 0;
+                            st.ebest = e;
+                            copy_vec(xbest, wx, dim, g);
+                            st.e_cur = e;
+                            copy_vec(x_cur, wx, dim, g);
+                        } else if (st.not_improved_idx >= st.not_improved_max_idx) {  // :261-262
+                            ls_req = kLsFromMin;
+                        }
+                    } else {
+                        ls_req = kLsNone;
+                        if (ok) copy_vec(xmin, wx, dim, g);                          // :265
+                        st.emin = e;
+                        st.not_improved_idx = 0;
+                        st.not_improved_max_idx = dim;
+                        if (e < st.ebest) {                                          // :269-273
+                            st.ebest = st.emin;
+                            copy_vec(xbest, wx, dim, g);
+                            st.e_cur = e;
+                            copy_vec(x_cur, wx, dim, g);
+                        }
+                    }
+                    if (!finished && (double)st.ncall >= a.maxfun) step_i = 0;        // :417-418
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- phase 5: SDARunner.result :420-428 ----------------------------------------------------
+        if (have && finished) {
+            if constexpr (TAPE) { if (rng.t.exhausted) err |= SDA_CHAIN_TAPE_EXHAUSTED; }
+            if (g.gl == 0) {
+                a.out.fun[chain] = st.ebest;
+                a.out.nit[chain] = iter;
+                a.out.ncall[chain] = st.ncall;
+                a.out.status[chain] = err;
+                if (a.out.ncall_ls) a.out.ncall_ls[chain] = st.ncall_ls;
+                if (a.out.n_ls) a.out.n_ls[chain] = st.n_ls;
+                if (a.out.hit) a.out.hit[chain] = st.hit;
+                if (a.out.ncall_hit) a.out.ncall_hit[chain] = st.ncall_hit;
+                if (a.out.f_hit) a.out.f_hit[chain] = st.f_hit;
+                if constexpr (TAPE) { if (a.out.tape_used) a.out.tape_used[chain] = rng.t.pos; }
+                else { if (a.out.tape_used) a.out.tape_used[chain] = 0; }
+            }
+            have = false;
+            pending = kNone;
+        }
         __syncwarp();
     }
 }
 
-// objective evaluation at n points, one warp per point
+// objective evaluation at n points, one chain group (G lanes, as in the annealing kernel) per point
 __global__ void __launch_bounds__(256) sda_eval_kernel(int functor, int dim, const double *params,
-                                                       const double *x, long long n, double *f)
+                                                       const double *x, long long n, double *f, int G)
 {
     const int lane = threadIdx.x & 31;
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long p = wid; p < n; p += nw) {
-        const double v = eval_objective(functor, x + p * dim, dim, params, lane);
-        if (lane == 0) f[p] = v;
+    const Group g = make_group(G, lane);
+    const long long gidx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) / G;
+    const long long rounds = (n + ngroups - 1) / ngroups;
+    for (long long r = 0; r < rounds; ++r) {
+        const long long p = gidx + r * ngroups;
+        if (p < n) {
+            const double v = eval_objective(functor, x + p * dim, dim, params, g);
+            if (g.gl == 0) f[p] = v;
+        }
     }
 }
 
@@ -403,13 +505,30 @@ static long long table_entries(const SdaConfig *c)
     return n > 0 ? n : 1;
 }
 
+// lanes per chain: the smallest power of two that leaves at most 8 coordinates per lane, so that
+// D=50 runs 4 chains per warp with 7 coordinates per lane (89 % of the lanes busy in the O(D)
+// loops instead of 78 % with one chain per warp) and warp-uniform work is shared by 32/G chains.
+// Tape replay is serial by construction and keeps one chain per warp.
+static int pick_group(int dim, int rng_mode)
+{
+    if (rng_mode == SDA_RNG_TAPE) return 32;
+    const char *env = getenv("SDA_GROUP");
+    if (env) {
+        const int g = atoi(env);
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
+    }
+    int g = 1;
+    while (g < 32 && (dim + g - 1) / g > 8) g <<= 1;
+    return g;
+}
+
 struct LaunchPlan {
-    int warps_per_block, blocks;
+    int warps_per_block, blocks, group;
     size_t smem;
     long long slots;
 };
 
-static int plan_launch(int dim, long long n_chains, int pure_sa, LaunchPlan *lp)
+static int plan_launch(int dim, long long n_chains, int pure_sa, int group, LaunchPlan *lp)
 {
     int dev = 0, sms = 0, smem_max = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -419,9 +538,13 @@ static int plan_launch(int dim, long long n_chains, int pure_sa, LaunchPlan *lp)
     e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
     int wpb = 8;
+    const int ng = 32 / group;
     const size_t ls_per_warp = pure_sa ? 0 : (size_t)sda::ls_smem_doubles() * sizeof(double);
-    while (wpb > 1 && (size_t)(4 + 3 * wpb) * dim * sizeof(double) + wpb * ls_per_warp > (size_t)smem_max) wpb >>= 1;
-    size_t smem = (size_t)(4 + 3 * wpb) * dim * sizeof(double) + wpb * ls_per_warp;
+    // aim for SDA_ANNEAL_MIN_BLOCKS resident blocks: shrink the block before giving up residency
+    const size_t budget = (size_t)smem_max / SDA_ANNEAL_MIN_BLOCKS - 1024;
+    while (wpb > 1 && (size_t)(4 + 3 * ng * wpb) * dim * sizeof(double) + wpb * ls_per_warp > budget) wpb >>= 1;
+    size_t smem = (size_t)(4 + 3 * ng * wpb) * dim * sizeof(double) + wpb * ls_per_warp;
+    lp->group = group;
     if (smem > (size_t)smem_max) return SDA_E_UNSUPPORTED;
     // resident blocks per SM: bounded by shared memory and by 2048 threads
     int bps = (int)((size_t)(smem_max) / (smem + 1024));
@@ -429,7 +552,7 @@ static int plan_launch(int dim, long long n_chains, int pure_sa, LaunchPlan *lp)
     int max_bps = 64 / wpb; // 64 warps per SM
     if (max_bps > SDA_ANNEAL_MIN_BLOCKS * 8 / wpb) max_bps = SDA_ANNEAL_MIN_BLOCKS * 8 / wpb; // register budget
     if (bps > max_bps) bps = max_bps;
-    long long want = (n_chains + wpb - 1) / wpb;
+    long long want = (n_chains + (long long)wpb * ng - 1) / ((long long)wpb * ng);
     long long blocks = (long long)sms * bps;
     if (blocks > want) blocks = want;
     if (blocks < 1) blocks = 1;
@@ -496,7 +619,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     if (c->rng_mode == SDA_RNG_TAPE && (!tape || tape_len <= 0)) return SDA_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     LaunchPlan lp;
-    rc = plan_launch(p->dim, n_chains, c->pure_sa, &lp);
+    rc = plan_launch(p->dim, n_chains, c->pure_sa, pick_group(p->dim, c->rng_mode), &lp);
     if (rc) return rc;
     size_t off_temp, off_sig, off_xmin, off_ls;
     long long ls_stride;
@@ -544,6 +667,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     if (lsmax < 100) lsmax = 100;
     if (lsmax > 1000) lsmax = 1000;
     a.ls_maxiter = lsmax;
+    a.group = lp.group;
 
     const int threads = lp.warps_per_block * 32;
     if (c->rng_mode == SDA_RNG_TAPE) {
@@ -638,7 +762,8 @@ extern "C" int sda_eval(const SdaProblem *p, const double *x, int64_t n, double 
     if (p->functor < 0 || p->functor >= SDA_FN_COUNT) return SDA_E_INVALID;
     long long blocks = (n + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    sda::sda_eval_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p->functor, p->dim, p->params, x, n, f);
+    sda::sda_eval_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p->functor, p->dim, p->params, x, n, f,
+                                                                       pick_group(p->dim, SDA_RNG_PHILOX));
     CK(cudaGetLastError());
     return SDA_OK;
 }

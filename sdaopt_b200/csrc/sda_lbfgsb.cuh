@@ -29,16 +29,17 @@ constexpr int kLsMaxls = 100;
 constexpr int kLsMaxfun = 15000;
 constexpr double kGradEps = 1.e-6;   // self.reps                                   :315
 
-// global (L1/L2) part of a warp's workspace: ws, wy | z r d t xp g x xl gl | 3 int arrays
+// global (L1/L2) part of a warp's workspace: ws, wy | z r d t xp g x xl gl | 3 int arrays | snd
 __host__ __device__ inline long long ls_workspace_doubles(int n)
 {
     const int m = kLsM;
-    return 2LL * m * n + 9LL * n + 2LL * n + 8;
+    return 2LL * m * n + 9LL * n + 2LL * n + 8 + 4LL * m * m;
 }
-// shared-memory part: sy ss wt (m x m) | wn snd (2m x 2m) | wa (8m).  These are updated in place
+// shared-memory part: sy ss wt (m x m) | wn (2m x 2m) | wa (8m).  These are updated in place
 // element by element (Cholesky, triangular solves, running sums); through global memory every
 // read-after-write would pay an L2 round trip because stores write through and drop the L1 line.
-__host__ __device__ constexpr int ls_smem_doubles() { return 3 * kLsM * kLsM + 8 * kLsM * kLsM + 8 * kLsM; }
+// (snd, the 2m x 2m accumulator of formk, is only read-modify-written once per element: global.)
+__host__ __device__ constexpr int ls_smem_doubles() { return 3 * kLsM * kLsM + 4 * kLsM * kLsM + 8 * kLsM; }
 
 struct LsWork {
     int n;
@@ -55,7 +56,7 @@ struct LsWork {
         n = n_;
         double *q = sbase;
         sy = q; q += m * m;  ss = q; q += m * m;  wt = q; q += m * m;
-        wn = q; q += 4 * m * m;  snd = q; q += 4 * m * m;
+        wn = q; q += 4 * m * m;
         wa = q;
         q = base;
         ws = q; q += (long long)m * n;  wy = q; q += (long long)m * n;
@@ -65,6 +66,7 @@ struct LsWork {
         index = reinterpret_cast<int *>(q);
         iwhere = index + n;
         indx2 = iwhere + n;
+        snd = q + 2 * n + 4;
     }
 };
 
@@ -882,7 +884,7 @@ __device__ __noinline__ bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st
             if (lane == 0) xe[i] = xp;
             __syncwarp();
         }
-        const double fe = func_wrapper<true>(a, st, xe, lane);
+        const double fe = func_wrapper<true>(a, st, xe, make_group(SDA_WARP, lane));
         if (st.stop) { if (e == 0) f = fe; return true; }
         if (e == 0) { f = fe; continue; }
         if (plus) { f1 = fe; continue; }
