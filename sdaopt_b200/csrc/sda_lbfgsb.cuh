@@ -860,39 +860,53 @@ __device__ __noinline__ bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st
     }
     for (int k = lane; k < n; k += SDA_WARP) xe[k] = x[k];
     __syncwarp();
-    // evaluation e = 0 is f(x); e = 2i+1 / 2i+2 are f(x + h_r e_i) / f(x - h_l e_i) -- one call
-    // site for all 1 + 2n evaluations (code size), in the reference's order (call counting)
-    double f1 = 0.0, denom = 0.0;
-    for (int e = 0; e <= 2 * n; ++e) {
-        const int i = (e - 1) >> 1;
-        const bool plus = (e & 1) != 0;
-        double xi = 0.0;
-        if (e > 0) {
-            xi = x[i];
-            double xp;
-            if (plus) {
-                double respr = kGradEps;
-                xp = xi + respr;
-                if (xp > up[i]) { xp = up[i]; respr = xp - xi; }
-                denom = respr;
-            } else {
-                double respl = kGradEps;
-                xp = xi - respl;
-                if (xp < lo[i]) { xp = lo[i]; respl = xi - xp; }
-                denom = respl + denom;                       // (respl + respr)
+    f = func_wrapper<true>(a, st, xe, make_group(SDA_WARP, lane));   // ScalarFunction: f, then jac
+    if (st.stop) return true;
+    // The 2n finite-difference evaluations f(x + h_r e_i), f(x - h_l e_i), 32 at a time: lane L of
+    // round r evaluates point e = 32 r + L by itself (even e: plus side of i = e/2, odd: minus).
+    // Call counting and the suite monitor see them in the reference's order (:340-341).
+    const long long mc0 = st.mon_calls;
+    for (int e0 = 0; e0 < 2 * n; e0 += SDA_WARP) {
+        const int e = e0 + lane;
+        const bool valid = e < 2 * n;
+        const int i = valid ? (e >> 1) : 0;
+        const bool plus = (e & 1) == 0;
+        const double xi = x[i];
+        double respr = kGradEps, respl = kGradEps;
+        double x1 = xi + respr;
+        if (x1 > up[i]) { x1 = up[i]; respr = x1 - xi; }
+        double x2 = xi - respl;
+        if (x2 < lo[i]) { x2 = lo[i]; respl = xi - x2; }
+        double fe = 0.0;
+        if (valid) fe = eval_objective_solo_ool(a.functor, xe, i, plus ? x1 : x2, n, a.params, lane);
+        if (a.max_calls > 0) {
+            const unsigned budget = __ballot_sync(SDA_FULL_MASK, valid && (mc0 + e + 1 >= a.max_calls));
+            const unsigned hits = __ballot_sync(SDA_FULL_MASK, valid && (fe <= a.fglob_tol));
+            const unsigned any = budget | hits;
+            if (any) {
+                const int first = __ffs(any) - 1;
+                const long long calls = e0 + first + 1;
+                st.ncall += calls; st.ncall_ls += calls; st.mon_calls = mc0 + calls;
+                if (!((budget >> first) & 1u)) {                 // bench.py:314-320
+                    st.hit = 1;
+                    st.ncall_hit = st.mon_calls;
+                    st.f_hit = __shfl_sync(SDA_FULL_MASK, fe, first);
+                }
+                st.stop = 1;
+                return true;
             }
-            if (lane == 0) xe[i] = xp;
-            __syncwarp();
         }
-        const double fe = func_wrapper<true>(a, st, xe, make_group(SDA_WARP, lane));
-        if (st.stop) { if (e == 0) f = fe; return true; }
-        if (e == 0) { f = fe; continue; }
-        if (plus) { f1 = fe; continue; }
-        double gi = (f1 - fe) / denom;
-        if (isnan(gi) || isinf(gi)) gi = 101.0;
-        __syncwarp();
-        if (lane == 0) { xe[i] = xi; g[i] = gi; w.gl[i] = gi; }
+        const double f2 = __shfl_down_sync(SDA_FULL_MASK, fe, 1);
+        if (valid && plus) {
+            double gi = (fe - f2) / (respl + respr);
+            if (isnan(gi) || isinf(gi)) gi = 101.0;
+            g[i] = gi;
+            w.gl[i] = gi;
+        }
     }
+    st.ncall += 2 * n; st.ncall_ls += 2 * n;
+    if (a.max_calls > 0) st.mon_calls = mc0 + 2 * n;
+    __syncwarp();
     for (int k = lane; k < n; k += SDA_WARP) w.xl[k] = x[k];
     w.fl = f;
     w.cache_valid = 1;

@@ -13,7 +13,8 @@ namespace sda {
 
 // suttonchen.py:23-40  (A=1, C=39.432, M=6, K=9).  Lane L owns atoms L, L+32, ...: for each it
 // accumulates sum_j r_ij^-9 and sum_j r_ij^-6 over all other atoms from shared memory.
-__device__ __forceinline__ double eval_sutton_chen(const double *x, int dim, const Group &g)
+template <class XV>
+__device__ __forceinline__ double eval_sutton_chen(const XV &x, int dim, const Group &g)
 {
     const int n = dim / 3;
     double part = 0.0;
@@ -35,7 +36,9 @@ __device__ __forceinline__ double eval_sutton_chen(const double *x, int dim, con
 }
 
 // Evaluate objective `fid` at x[0..dim).  Warp-uniform arguments; warp-uniform result.
-__device__ __forceinline__ double eval_objective(int fid, const double *x, int dim,
+// x is anything indexable: a pointer into shared memory, or a PerturbedView of it.
+template <class XV>
+__device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
                                                  const double *params, const Group &g)
 {
     const int lane = g.gl, SDA_STRIDE = g.G;
@@ -104,6 +107,15 @@ __device__ __forceinline__ double eval_objective(int fid, const double *x, int d
     }
 }
 
+// x with one coordinate replaced: the finite-difference points x +- h e_i of the gradient
+// (_sda.py:328-339) without a private copy of x per lane
+struct PerturbedView {
+    const double *x;
+    int index;
+    double value;
+    __device__ __forceinline__ double operator[](int k) const { return k == index ? value : x[k]; }
+};
+
 // Out-of-line copy for the cold callers (local search, (re)initialisation): the body with all
 // registered objectives is ~4.5 K instructions, and inlining it at every call site grew the
 // L-BFGS-B code to 750 KB -- ncu showed 85 % of its cycles stalled on instruction fetch.
@@ -111,6 +123,16 @@ __device__ __noinline__ double eval_objective_ool(int fid, const double *x, int 
                                                   const double *params, int G, int lane)
 {
     return eval_objective(fid, x, dim, params, make_group(G, lane));
+}
+
+// One lane evaluates one perturbed point by itself (G = 1): the 2*D finite-difference evaluations
+// of a gradient run 32 at a time.
+__device__ __noinline__ double eval_objective_solo_ool(int fid, const double *x, int index,
+                                                       double value, int dim, const double *params,
+                                                       int lane)
+{
+    const PerturbedView v = { x, index, value };
+    return eval_objective(fid, v, dim, params, make_group(1, lane));
 }
 
 }  // namespace sda
