@@ -116,7 +116,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_chains = max(cores, 8) * 2
+    n_chains = max(cores, 8) * 8
     vals, times = [], []
     for it in range(args.warmup + args.steps):
         evals, dt, _ = cpu_reference_run(n_chains, cores, args.maxiter, args.pure_sa)
@@ -271,7 +271,7 @@ def run_ours(args):
         cpu = None
         if world == 1 or True:
             cores = os.cpu_count() or 1
-            n = max(cores, 8) * 2
+            n = max(cores, 8) * 8
             ce, cdt, _ = cpu_reference_run(n, cores, args.maxiter, args.pure_sa)
             cpu = {"value": ce / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d chains x maxiter=%d of the same workload, %.1f s, oracle/ C port on "

@@ -330,3 +330,31 @@ def test_full_size_batch_properties(sb):
     F = f(r1.x[::64])
     np.testing.assert_allclose(F, r1.fun[::64], rtol=1e-13)
     assert len(np.unique(r1.fun)) > 0.99 * n           # independent streams
+
+
+# ---- suite runner (config 5 slice): one launch per job, BenchUnit pickles + results.csv ----------------
+def test_suite_runner_writes_reference_format(sb, oracle, tmp_path):
+    import csv
+    from sdaopt_b200.benchmark import Benchmarker, report
+    from sdaopt_b200.benchmark import benchunit
+    folder = str(tmp_path / "DATA")
+    units = Benchmarker(20, folder, names=["Rastrigin", "Sphere"], max_calls=100000).run()
+    assert len(units) == 2 + 11                                  # Rastrigin is in the n-D selection
+    by_name = {u.name: u for u in units}
+    assert os.path.exists(os.path.join(folder, "Rastrigin_10-SDA-20.data"))
+    u = benchunit.load(os.path.join(folder, "Rastrigin-SDA-20.data"))
+    assert u.success.all() and 100 <= u.medall <= 3000          # App. C.7: 166..694 on the reference
+    assert by_name["Sphere"].success.all() and by_name["Sphere"].medall < 100
+    assert by_name["Rastrigin_10"].success.mean() >= 0.9 and 2000 < by_name["Rastrigin_10"].med < 9000
+    # the same seeds through the oracle: same first hits on most runs
+    f = sb.Rastrigin(2)
+    o = oracle.run(oracle.Problem("Rastrigin", f.bounds), 20, seeds=np.arange(20, dtype=np.uint64) + np.uint64(1234),
+                   maxiter=int(1e6), max_calls=100000, fglob=0.0, tol=1e-8,
+                   tables=sb._sda.temperature_tables(int(1e6)))
+    assert np.mean(u.values()["ncall"] == o["ncall_hit"]) >= 0.6
+    out = os.path.join(folder, "results.csv")
+    report(folder, kind="csv", path=out)
+    rows = list(csv.reader(open(out), delimiter=",", quotechar="|"))
+    assert len(rows) == 14 and rows[0][0] == "Function name"
+    # a second run skips existing files (bench.py:164-167)
+    assert Benchmarker(20, folder, names=["Rastrigin", "Sphere"], max_calls=100000).run() == []
