@@ -135,28 +135,31 @@ __device__ __noinline__ int ls_bmv(LsWork &w, int col, const double *v, double *
 {
     const int m = kLsM;
     if (col == 0) return 0;
-    p[col] = v[col];
-    #pragma unroll 1
-    for (int i = 2; i <= col; ++i) {
-        const int i2 = col + i;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane == 0) p[col] = v[col];
+    if (lane >= 1 && lane < col) {           // row i = lane + 1 of L D^-1 v1 (serial formula per row)
+        const int i = lane + 1, i2 = col + i;
         double sum = 0.0;
         #pragma unroll 1
         for (int k = 1; k <= i - 1; ++k) sum += LSY(i, k) * v[k - 1] / LSY(k, k);
         p[i2 - 1] = v[i2 - 1] + sum;
     }
+    __syncwarp();
     if (tri_solve_upper(w.wt, m, col, p + col, 1)) return 1;
     #pragma unroll 1
     for (int i = 1; i <= col; ++i) p[i - 1] = v[i - 1] / sqrt(LSY(i, i));
     if (tri_solve_upper(w.wt, m, col, p + col, 0)) return 1;
-    #pragma unroll 1
-    for (int i = 1; i <= col; ++i) p[i - 1] = -p[i - 1] / sqrt(LSY(i, i));
-    #pragma unroll 1
-    for (int i = 1; i <= col; ++i) {
+    __syncwarp();
+    if (lane < col) {
+        const int i = lane + 1;
+        double pi = -p[i - 1] / sqrt(LSY(i, i));
         double sum = 0.0;
         #pragma unroll 1
         for (int k = i + 1; k <= col; ++k) sum += LSY(k, i) * p[col + k - 1] / LSY(i, i);
-        p[i - 1] += sum;
+        p[i - 1] = pi + sum;
     }
+    __syncwarp();
     return 0;
 }
 
@@ -481,37 +484,58 @@ __device__ __noinline__ int ls_formk(LsWork &w, int nsub, int nenter, int ileave
     }
     if (chol_upper(w.wn, m2, col)) return -1;
     const int col2 = 2 * col;
+    // the col right-hand sides of L^-1 (-L_a' + R_z') and the columns of the (2,2) block are
+    // independent: lane c owns column js = col + 1 + c (same operation order per column as the
+    // serial sweep, so the factors are bit-identical)
+    __syncwarp();
     #pragma unroll 1
-    for (int js = col + 1; js <= col2; ++js)
-        if (tri_solve_upper(w.wn, m2, col, &LWN(1, js), 1)) return -1;
-    #pragma unroll 1
-    for (int is = col + 1; is <= col2; ++is)
+    for (int j = 1; j <= col; ++j)
+        if (LWN(j, j) == 0.0) return -1;
+    if (lane < col) {
+        double *b = &LWN(1, col + 1 + lane);
+        b[0] = b[0] / LWN(1, 1);
         #pragma unroll 1
-        for (int js = is; js <= col2; ++js) {
+        for (int j = 2; j <= col; ++j) {
+            double dot = 0.0;
+            #pragma unroll 1
+            for (int i = 1; i <= j - 1; ++i) dot += LWN(i, j) * b[i - 1];
+            b[j - 1] = (b[j - 1] - dot) / LWN(j, j);
+        }
+    }
+    __syncwarp();
+    if (lane < col) {
+        const int js = col + 1 + lane;
+        #pragma unroll 1
+        for (int is = col + 1; is <= js; ++is) {
             double dot = 0.0;
             #pragma unroll 1
             for (int k = 1; k <= col; ++k) dot += LWN(k, is) * LWN(k, js);
             LWN(is, js) += dot;
         }
+    }
+    __syncwarp();
     if (chol_upper(&LWN(col + 1, col + 1), m2, col)) return -2;
     return 0;
 }
 
-__device__ __noinline__ int ls_formt(LsWork &w, int col, double theta)
+__device__ __noinline__ int ls_formt(LsWork &w, int col, double theta, int lane)
 {
     const int m = kLsM;
-    #pragma unroll 1
-    for (int j = 1; j <= col; ++j) LWT(1, j) = theta * LSS(1, j);
-    #pragma unroll 1
-    for (int i = 2; i <= col; ++i)
+    // lane j-1 builds column j of the upper triangle (element formulas unchanged)
+    __syncwarp();
+    if (lane < col) {
+        const int j = lane + 1;
+        LWT(1, j) = theta * LSS(1, j);
         #pragma unroll 1
-        for (int j = i; j <= col; ++j) {
-            const int k1 = (i < j ? i : j) - 1;
+        for (int i = 2; i <= j; ++i) {
+            const int k1 = i - 1;
             double ddum = 0.0;
             #pragma unroll 1
             for (int k = 1; k <= k1; ++k) ddum += LSY(i, k) * LSY(j, k) / LSY(k, k);
             LWT(i, j) = ddum + theta * LSS(i, j);
         }
+    }
+    __syncwarp();
     return chol_upper(w.wt, m, col) ? -3 : 0;
 }
 
@@ -1082,7 +1106,7 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
             } else {
                 updatd = 1; iupdat++;
                 ls_matupd(w, itail, iupdat, col, head, theta, rr, dr, stp, dtd, lane);
-                if (ls_formt(w, col, theta) != 0) {
+                if (ls_formt(w, col, theta, lane) != 0) {
                     info = 0; col = 0; head = 1; theta = 1.0; iupdat = 0; updatd = 0;
                 }
             }
