@@ -226,7 +226,7 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
     const int dim = a.dim;
     const int G = g.G;
     const double t_step = __ddiv_rn(temperature, (double)(step + 1));
-    const VisitConst vc = { sigmax, a.qv - 1.0, 3.0 - a.qv };
+    const VisitConst vc = { sigmax, a.qv - 1.0, 3.0 - a.qv, (a.qv - 1.0) / (3.0 - a.qv) };
     st.not_improved_idx += 1;
     for (long long j = 0; j < 2LL * dim; ++j) {
         if (j == 0) st.state_improved = 0;
@@ -262,8 +262,8 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                     double xg0, yg0, s0, xg1 = 0.5, yg1 = 0.5, s1 = 0.5;
                     polar_pair_philox(rng.p, (uint32_t)k0, xg0, yg0, s0);
                     if (two) polar_pair_philox(rng.p, (uint32_t)k1, xg1, yg1, s1);
-                    double v0 = visit_from_polar(xg0, yg0, s0, vc);
-                    double v1 = visit_from_polar(xg1, yg1, s1, vc);
+                    double v0 = visit_from_polar_fast(xg0, yg0, s0, vc);
+                    double v1 = visit_from_polar_fast(xg1, yg1, s1, vc);
                     if (!have_clip && (fabs(v0) > kTailLimit || (two && fabs(v1) > kTailLimit))) {
                         rng.p.pair(kClip, 0, 0, upper_sample, lower_sample);
                         have_clip = true;

@@ -141,6 +141,7 @@ struct VisitConst {
     double sigmax;   // sigmax(T), K1 table                               :76-86
     double qv_m1;    // qv - 1.0
     double three_mq; // 3.0 - qv
+    double c;        // (qv - 1) / (3 - qv), the exponent of |y| in the denominator
 };
 
 // gaussian_fn(1) / gaussian_fn(0) + visit_fn from one accepted polar pair   :87-91, :103-107
@@ -152,6 +153,20 @@ __device__ __forceinline__ double visit_from_polar(double xg, double yg, double 
     const double y = __dmul_rn(root, xg);                              // :88, :107
     const double den = exp(__ddiv_rn(__dmul_rn(vc.qv_m1, log(fabs(y))), vc.three_mq)); // :89-90
     return __ddiv_rn(x, den);                                          // :91
+}
+
+// Production (Philox) form of the same sample: visit = sigmax * g1 * |g0|^-c with
+// c = (qv-1)/(3-qv), i.e. x / exp(c ln|y|) = x * exp(-c ln|y|).  Algebraically identical to
+// visit_from_polar, one IEEE division instead of three; the results differ from the reference
+// order by a few ulp (the same size as the exp/log differences between math libraries), so the
+// tape-replay path keeps visit_from_polar and this form is validated against the oracle on the
+// same Philox keys (tests/test_gpu_parity.py::test_philox_chains_match_oracle).
+__device__ __forceinline__ double visit_from_polar_fast(double xg, double yg, double s,
+                                                        const VisitConst &vc)
+{
+    const double root = sqrt(-2.0 * log(s) / s);
+    const double y = root * xg;
+    return (vc.sigmax * (root * yg)) * exp(-vc.c * log(fabs(y)));
 }
 
 // C fmod(a, R) for R > 0, bit-exact, in ~8 FP64 instructions instead of libdevice's long-division
@@ -241,7 +256,7 @@ __device__ __forceinline__ double visit_sample_philox(const PhiloxRng &rng, uint
         yg = __dsub_rn(__dmul_rn(u2, 2.0), 1.0);
         s = __dadd_rn(__dmul_rn(xg, xg), __dmul_rn(yg, yg));
     } while (s <= 0.0 || s >= 1.0);
-    return visit_from_polar(xg, yg, s, vc);
+    return visit_from_polar_fast(xg, yg, s, vc);
 }
 
 // same from the tape (uniform across the warp)

@@ -328,7 +328,7 @@ __global__ void sda_visiting_kernel(DeviceArgs a, const double *x, long long ste
     const int dim = a.dim, lane = threadIdx.x & 31;
     double *sv = smem;
     TapeRng rng = { a.tape, 0, a.tape_len, false };
-    const VisitConst vc = { sigmax, a.qv - 1.0, 3.0 - a.qv };
+    const VisitConst vc = { sigmax, a.qv - 1.0, 3.0 - a.qv, (a.qv - 1.0) / (3.0 - a.qv) };
     if (step < dim) {
         for (int k = 0; k < dim; ++k) {
             const double v = visit_sample_tape(rng, vc);
@@ -364,7 +364,7 @@ __global__ void sda_visit_fn_kernel(double qv, double sigmax, const double *tape
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     TapeRng rng = { tape, 0, tape_len, false };
-    const VisitConst vc = { sigmax, qv - 1.0, 3.0 - qv };
+    const VisitConst vc = { sigmax, qv - 1.0, 3.0 - qv, (qv - 1.0) / (3.0 - qv) };
     for (long long i = 0; i < n; ++i) out[i] = visit_sample_tape(rng, vc);
     *tape_used = rng.exhausted ? -1 : rng.pos;
 }

@@ -260,8 +260,8 @@ __device__ __noinline__ int ls_cauchy(LsWork &w, const double *x, const double *
         p[lane] = (lane >= col && theta != 1.0) ? acc * theta : acc;
     }
     __syncwarp();
-    #pragma unroll 1
-    for (int i = 0; i < n; ++i) xcp[i] = x[i];
+    for (int i = lane; i < n; i += SDA_WARP) xcp[i] = x[i];
+    __syncwarp();
     if (nbreak == 0 && nfree == n + 1) return 0;
     #pragma unroll 1
     for (int j = 0; j < col2; ++j) c[j] = 0.0;
@@ -335,8 +335,9 @@ __device__ __noinline__ int ls_cauchy(LsWork &w, const double *x, const double *
     if (!skip_tail) {
         if (dtm <= 0.0) dtm = 0.0;
         tsum += dtm;
-        #pragma unroll 1
-        for (int i = 0; i < n; ++i) xcp[i] += tsum * d[i];
+        __syncwarp();
+        for (int i = lane; i < n; i += SDA_WARP) xcp[i] += tsum * d[i];
+        __syncwarp();
     }
     if (col > 0) for (int j = 0; j < col2; ++j) c[j] += dtm * p[j];
     return 0;
