@@ -447,11 +447,18 @@ static void markov_run(Chain *ch, int64_t step, double temperature, double sigma
             trace(ch, e, dec);
         } else {
             int dec = ORC_DEC_REJECT;
-            double r = rng_one(&ch->rng, PUR_ACCEPT, 0, 0);
             double pqa_temp = (qa - 1.0) * (e - ch->e_cur) / ch->temperature_step + 1.;
-            double pqa;
+            double pqa, r;
+            /* Reference: r is drawn first, always (_sda.py:216).  The tape replays that.  The
+             * Philox protocol shared with the CUDA path addresses draws, so the draw can be
+             * skipped when pqa == 0: r <= 0 needs r == 0.0 exactly (2^-53), defined as reject. */
+            if (ch->rng.mode == ORC_RNG_TAPE) r = rng_one(&ch->rng, PUR_ACCEPT, 0, 0);
+            else r = 2.0;
             if (pqa_temp < 0.) pqa = 0.;
-            else pqa = exp(log(pqa_temp) / (1. - qa));
+            else {
+                pqa = exp(log(pqa_temp) / (1. - qa));
+                if (ch->rng.mode != ORC_RNG_TAPE) r = rng_one(&ch->rng, PUR_ACCEPT, 0, 0);
+            }
             if (r <= pqa) {
                 ch->e_cur = e;
                 memcpy(ch->x_cur, ch->x_visit, sizeof(double) * dim);

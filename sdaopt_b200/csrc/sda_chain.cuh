@@ -167,8 +167,13 @@ __device__ __forceinline__ void trace(const DeviceArgs &a, ChainState &st, long 
 
 // K4: generalized Metropolis acceptance + best / stagnation bookkeeping            :204-233
 // x_vis holds the proposal; `single` >= 0 names the only coordinate that differs from x_cur.
+// The acceptance uniform r is supplied by `draw_r` only on the non-improving branch (:216).  With
+// the counter-based stream it is additionally skipped when pqa == 0: r <= 0 holds only for
+// r == 0.0 exactly (probability 2^-53), which the Philox protocol (and the oracle's Philox mode)
+// define as a rejection; the tape replay always consumes the uniform like the reference.
+template <bool TAPE, class DrawR>
 __device__ __forceinline__ void accept_step(const DeviceArgs &a, ChainState &st, long long chain,
-                                            double e, double r, double t_step, long long j,
+                                            double e, DrawR draw_r, double t_step, long long j,
                                             int single, double *x_cur, double *x_vis,
                                             double *xbest, double *xmin, const Group &g)
 {
@@ -192,9 +197,16 @@ __device__ __forceinline__ void accept_step(const DeviceArgs &a, ChainState &st,
         const double pqa_temp =
             __dadd_rn(__ddiv_rn(__dmul_rn(a.qa - 1.0, __dsub_rn(e, st.e_cur)), t_step), 1.);
         double pqa;
-        if (pqa_temp < 0.) pqa = 0.;
-        else pqa = exp(__ddiv_rn(log(pqa_temp), 1. - a.qa));
-        if (r <= pqa) {
+        bool accept;
+        if (pqa_temp < 0.) {
+            pqa = 0.;
+            if constexpr (TAPE) accept = draw_r() <= pqa;
+            else accept = false;
+        } else {
+            pqa = exp(__ddiv_rn(log(pqa_temp), 1. - a.qa));
+            accept = draw_r() <= pqa;
+        }
+        if (accept) {
             st.e_cur = e;
             if (single >= 0) { if (g.gl == 0) x_cur[single] = x_vis[single]; }
             else copy_vec(x_cur, x_vis, dim, g);
@@ -318,12 +330,12 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
         const double e = func_wrapper<false>(a, st, x_vis, g);
         if (st.stop) return;
         // ---- K4: acceptance.  The uniform is drawn only when e >= E_cur          :216
-        double r = 0.0;
-        if (!(e < st.e_cur)) {
-            if constexpr (TAPE) { r = rng.t.next(); if (rng.t.exhausted) return; }
-            else { double r2; rng.p.pair(kAccept, 0, 0, r, r2); }
-        }
-        accept_step(a, st, chain, e, r, t_step, j, single, x_cur, x_vis, xbest, xmin, g);
+        auto draw_r = [&]() -> double {
+            if constexpr (TAPE) { return rng.t.next(); }
+            else { double r, r2; rng.p.pair(kAccept, 0, 0, r, r2); return r; }
+        };
+        accept_step<TAPE>(a, st, chain, e, draw_r, t_step, j, single, x_cur, x_vis, xbest, xmin, g);
+        if constexpr (TAPE) { if (rng.t.exhausted) return; }
     }
 }
 

@@ -39,8 +39,11 @@ struct Philox {
         uint32_t a0 = k0, a1 = k1;
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
-            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            // one IMAD.WIDE per product: both halves come out of the same 32x32->64 multiply
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+            const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+            const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+            const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
             c0 = hi1 ^ c1 ^ a0;
             c1 = lo1;
             c2 = hi0 ^ c3 ^ a1;
