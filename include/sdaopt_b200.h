@@ -58,6 +58,56 @@ enum {
     SDA_FN_CONSTANT = 8,          /* tests/test_sda.py:34 `weirdfunc`; params[0] = value */
     SDA_FN_SPHERE = 9,            /* go_funcs_S.py:1156-1159 */
     SDA_FN_GRIEWANK = 10,         /* go_funcs_G.py:171-175 */
+    /* catalogue widening: go_benchmark_functions/go_funcs_*.py, same class names */
+    SDA_FN_ALPINE01 = 11,
+    SDA_FN_BROWN = 12,
+    SDA_FN_CIGAR = 13,
+    SDA_FN_COSINE_MIXTURE = 14,
+    SDA_FN_DEB01 = 15,
+    SDA_FN_DIXON_PRICE = 16,
+    SDA_FN_EASOM = 17,
+    SDA_FN_QING = 18,
+    SDA_FN_QUINTIC = 19,
+    SDA_FN_SALOMON = 20,
+    SDA_FN_SCHWEFEL20 = 21,
+    SDA_FN_SCHWEFEL21 = 22,
+    SDA_FN_SCHWEFEL22 = 23,
+    SDA_FN_STEP = 24,
+    SDA_FN_STYBLINSKI_TANG = 25,
+    SDA_FN_TRID = 26,
+    SDA_FN_ZACHAROV = 27,
+    SDA_FN_SIX_HUMP_CAMEL = 28,
+    SDA_FN_BEALE = 29,
+    SDA_FN_HIMMEL_BLAU = 30,
+    SDA_FN_MATYAS = 31,
+    SDA_FN_MC_CORMICK = 32,
+    SDA_FN_GOLDSTEIN_PRICE = 33,
+    SDA_FN_LEVY13 = 34,
+    SDA_FN_BOHACHEVSKY1 = 35,
+    SDA_FN_BUKIN06 = 36,
+    SDA_FN_EGG_CRATE = 37,
+    SDA_FN_SCHAFFER01 = 38,
+    SDA_FN_DROP_WAVE = 39,
+    SDA_FN_THREE_HUMP_CAMEL = 40,
+    SDA_FN_ZETTL = 41,
+    SDA_FN_LEON = 42,
+    SDA_FN_CUBE = 43,
+    SDA_FN_BRENT = 44,
+    SDA_FN_PRICE01 = 45,
+    SDA_FN_BIRD = 46,
+    SDA_FN_ACKLEY02 = 47,
+    SDA_FN_ACKLEY03 = 48,
+    SDA_FN_ZIRILLI = 49,
+    SDA_FN_WAVY = 50,
+    SDA_FN_STEP2 = 51,
+    SDA_FN_PLATEAU = 52,
+    SDA_FN_SODP = 53,
+    SDA_FN_TRIGONOMETRIC02 = 54,
+    SDA_FN_XIN_SHE_YANG02 = 55,
+    SDA_FN_SINE_ENVELOPE = 56,
+    SDA_FN_PATHOLOGICAL = 57,
+    SDA_FN_RANA = 58,
+    SDA_FN_ADJIMAN = 59,
     SDA_FN_COUNT
 };
 

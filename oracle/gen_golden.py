@@ -228,6 +228,21 @@ def gen_objective_points():
             F = np.array([k.fun(x) for x in X])
             rows.append(dict(functor=name, dim=D, params=np.zeros(0), X=X, F=F, fglob=k.fglob,
                              bounds=np.array(k.bounds, dtype=float)))
+    # catalogue widening: default dimension, plus D = 7 and 40 where the class is n-D
+    from sdaopt_b200.functors import _CATALOGUE2
+    for name, (n_default, nd, _box, _f) in sorted(_CATALOGUE2.items()):
+        for D in ([n_default, 7, 40] if nd else [n_default]):
+            k = getattr(gbf, name)(dimensions=D) if nd else getattr(gbf, name)()
+            lo = np.array([b[0] for b in k.bounds], dtype=float)
+            up = np.array([b[1] for b in k.bounds], dtype=float)
+            X = lo + rs.random_sample((16, k.N)) * (up - lo)
+            if k.global_optimum is not None and len(k.global_optimum[0]) == k.N:
+                X[0] = np.array(k.global_optimum[0], dtype=float)
+            X[1] = lo
+            X[2] = up
+            F = np.array([float(k.fun(x)) for x in X])
+            rows.append(dict(functor=name, dim=k.N, params=np.zeros(0), X=X, F=F, fglob=k.fglob,
+                             bounds=np.array(k.bounds, dtype=float)))
     D = 50
     X = -5.12 + rs.random_sample((16, D)) * 15.36
     rows.append(dict(functor="ShiftedRastrigin", dim=D, params=np.array([3.14159]), X=X,
@@ -317,7 +332,11 @@ def gen_asrun_summary():
 
 
 if __name__ == "__main__":
-    if MODE == "libm":
+    if MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "objectives":
+        gen_objective_points()
+    elif os.environ.get("SDA_GOLDEN_ONLY"):
+        pass
+    elif MODE == "libm":
         gen_sampler()
         gen_objective_points()
         gen_trajectories()

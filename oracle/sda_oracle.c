@@ -221,6 +221,174 @@ double orc_eval(const OrcProblem *p, const double *x)
         }
         s = np_sum(t, n);
         return s / 4000.0 - pr + 1.0;
+
+    /* ---- catalogue widening: go_funcs_<initial>.py, one case per class `fun` ---- */
+    case ORC_FN_ALPINE01:
+        for (int i = 0; i < n; ++i) t[i] = fabs(x[i] * sin(x[i]) + 0.1 * x[i]);
+        return np_sum(t, n);
+    case ORC_FN_BROWN:
+        for (int i = 0; i + 1 < n; ++i) {
+            double x0 = x[i] * x[i], x1 = x[i + 1] * x[i + 1];
+            t[i] = pow(x0, x1 + 1.0) + pow(x1, x0 + 1.0);
+        }
+        return np_sum(t, n - 1);
+    case ORC_FN_CIGAR:
+        for (int i = 1; i < n; ++i) t[i - 1] = x[i] * x[i];
+        return x[0] * x[0] + 1e6 * np_sum(t, n - 1);
+    case ORC_FN_COSINE_MIXTURE:
+        for (int i = 0; i < n; ++i) { t[i] = cos(5.0 * M_PI * x[i]); t2[i] = x[i] * x[i]; }
+        return -0.1 * np_sum(t, n) - np_sum(t2, n);
+    case ORC_FN_DEB01:
+        for (int i = 0; i < n; ++i) t[i] = pow(sin(5 * M_PI * x[i]), 6.0);
+        return -(1.0 / n) * np_sum(t, n);
+    case ORC_FN_DIXON_PRICE:
+        for (int i = 1; i < n; ++i) { double d = 2.0 * x[i] * x[i] - x[i - 1]; t[i - 1] = (i + 1) * (d * d); }
+        return np_sum(t, n - 1) + (x[0] - 1.0) * (x[0] - 1.0);
+    case ORC_FN_QING:
+        for (int i = 0; i < n; ++i) { double d = x[i] * x[i] - (i + 1); t[i] = d * d; }
+        return np_sum(t, n);
+    case ORC_FN_QUINTIC:
+        for (int i = 0; i < n; ++i) {
+            double v = x[i];
+            t[i] = fabs(pow(v, 5) - 3 * pow(v, 4) + 4 * pow(v, 3) + 2 * v * v - 10 * v - 4);
+        }
+        return np_sum(t, n);
+    case ORC_FN_SALOMON: {
+        for (int i = 0; i < n; ++i) t[i] = x[i] * x[i];
+        double u = sqrt(np_sum(t, n));
+        return 1 - cos(2 * M_PI * u) + 0.1 * u;
+    }
+    case ORC_FN_SCHWEFEL20:
+        for (int i = 0; i < n; ++i) t[i] = fabs(x[i]);
+        return np_sum(t, n);
+    case ORC_FN_SCHWEFEL21:
+        for (int i = 0; i < n; ++i) s = fmax(s, fabs(x[i]));
+        return s;
+    case ORC_FN_SCHWEFEL22:
+        for (int i = 0; i < n; ++i) { t[i] = fabs(x[i]); pr *= fabs(x[i]); }
+        return np_sum(t, n) + pr;
+    case ORC_FN_STEP:
+        for (int i = 0; i < n; ++i) t[i] = floor(fabs(x[i]));
+        return np_sum(t, n);
+    case ORC_FN_STYBLINSKI_TANG:
+        for (int i = 0; i < n; ++i) t[i] = pow(x[i], 4) - 16 * x[i] * x[i] + 5 * x[i];
+        return np_sum(t, n) / 2;
+    case ORC_FN_TRID:
+        for (int i = 0; i < n; ++i) t[i] = (x[i] - 1.0) * (x[i] - 1.0);
+        for (int i = 1; i < n; ++i) t2[i - 1] = x[i] * x[i - 1];
+        return np_sum(t, n) - np_sum(t2, n - 1);
+    case ORC_FN_ZACHAROV: {
+        for (int i = 0; i < n; ++i) { t[i] = x[i] * x[i]; t2[i] = (i + 1) * x[i]; }
+        double u = np_sum(t, n), v = np_sum(t2, n);
+        return u + pow(0.5 * v, 2) + pow(0.5 * v, 4);
+    }
+    case ORC_FN_WAVY:
+        for (int i = 0; i < n; ++i) t[i] = cos(10 * x[i]) * exp(-(x[i] * x[i]) / 2.0);
+        return 1.0 - (1.0 / n) * np_sum(t, n);
+    case ORC_FN_STEP2:
+        for (int i = 0; i < n; ++i) { double d = floor(x[i]) + 0.5; t[i] = d * d; }
+        return np_sum(t, n);
+    case ORC_FN_PLATEAU:
+        for (int i = 0; i < n; ++i) t[i] = floor(fabs(x[i]));
+        return 30.0 + np_sum(t, n);
+    case ORC_FN_SODP:
+        for (int i = 0; i < n; ++i) t[i] = pow(fabs(x[i]), i + 2);
+        return np_sum(t, n);
+    case ORC_FN_TRIGONOMETRIC02:
+        for (int i = 0; i < n; ++i) {
+            double d = (x[i] - 0.9) * (x[i] - 0.9);
+            t[i] = 8 * pow(sin(7 * d), 2) + 6 * pow(sin(14 * d), 2) + d;
+        }
+        return 1.0 + np_sum(t, n);
+    case ORC_FN_XIN_SHE_YANG02:
+        for (int i = 0; i < n; ++i) { t[i] = fabs(x[i]); t2[i] = sin(x[i] * x[i]); }
+        return np_sum(t, n) * exp(-np_sum(t2, n));
+    case ORC_FN_SINE_ENVELOPE:
+        for (int i = 0; i + 1 < n; ++i) {
+            double q = x[i] * x[i] + x[i + 1] * x[i + 1];
+            t[i] = (pow(sin(sqrt(q)), 2) - 0.5) / pow(1 + 0.001 * q, 2) + 0.5;
+        }
+        return np_sum(t, n - 1);
+    case ORC_FN_PATHOLOGICAL:
+        for (int i = 0; i + 1 < n; ++i) {
+            double a0 = x[i], a1 = x[i + 1];
+            t[i] = 0.5 + (pow(sin(sqrt(100 * a0 * a0 + a1 * a1)), 2) - 0.5) /
+                             (1. + 0.001 * pow(a0 * a0 - 2 * a0 * a1 + a1 * a1, 2));
+        }
+        return np_sum(t, n - 1);
+    case ORC_FN_RANA:
+        for (int i = 0; i + 1 < n; ++i) {
+            double a0 = x[i], a1 = x[i + 1];
+            double t1 = sqrt(fabs(a1 + a0 + 1)), tt2 = sqrt(fabs(a1 - a0 + 1));
+            t[i] = (a1 + 1) * cos(tt2) * sin(t1) + a0 * cos(t1) * sin(tt2);
+        }
+        return np_sum(t, n - 1);
+    case ORC_FN_EASOM: {
+        double a = pow(x[0] - M_PI, 2) + pow(x[1] - M_PI, 2);
+        return -cos(x[0]) * cos(x[1]) * exp(-a);
+    }
+    case ORC_FN_SIX_HUMP_CAMEL:
+        return (4 - 2.1 * x[0] * x[0] + pow(x[0], 4) / 3) * x[0] * x[0] + x[0] * x[1] +
+               (4 * x[1] * x[1] - 4) * x[1] * x[1];
+    case ORC_FN_BEALE:
+        return pow(1.5 - x[0] + x[0] * x[1], 2) + pow(2.25 - x[0] + x[0] * x[1] * x[1], 2) +
+               pow(2.625 - x[0] + x[0] * pow(x[1], 3), 2);
+    case ORC_FN_HIMMEL_BLAU:
+        return pow(x[0] * x[0] + x[1] - 11, 2) + pow(x[0] + x[1] * x[1] - 7, 2);
+    case ORC_FN_MATYAS:
+        return 0.26 * (x[0] * x[0] + x[1] * x[1]) - 0.48 * x[0] * x[1];
+    case ORC_FN_MC_CORMICK:
+        return sin(x[0] + x[1]) + pow(x[0] - x[1], 2) - 1.5 * x[0] + 2.5 * x[1] + 1;
+    case ORC_FN_GOLDSTEIN_PRICE: {
+        double a = 1 + pow(x[0] + x[1] + 1, 2) * (19 - 14 * x[0] + 3 * x[0] * x[0] - 14 * x[1] +
+                                                  6 * x[0] * x[1] + 3 * x[1] * x[1]);
+        double b = 30 + pow(2 * x[0] - 3 * x[1], 2) * (18 - 32 * x[0] + 12 * x[0] * x[0] + 48 * x[1] -
+                                                      36 * x[0] * x[1] + 27 * x[1] * x[1]);
+        return a * b;
+    }
+    case ORC_FN_LEVY13: {
+        double u = pow(sin(3 * M_PI * x[0]), 2);
+        double v = pow(x[0] - 1, 2) * (1 + pow(sin(3 * M_PI * x[1]), 2));
+        double w = pow(x[1] - 1, 2) * (1 + pow(sin(2 * M_PI * x[1]), 2));
+        return u + v + w;
+    }
+    case ORC_FN_BOHACHEVSKY1:
+        return x[0] * x[0] + 2 * x[1] * x[1] - 0.3 * cos(3 * M_PI * x[0]) - 0.4 * cos(4 * M_PI * x[1]) + 0.7;
+    case ORC_FN_BUKIN06:
+        return 100 * sqrt(fabs(x[1] - 0.01 * x[0] * x[0])) + 0.01 * fabs(x[0] + 10);
+    case ORC_FN_EGG_CRATE:
+        return x[0] * x[0] + x[1] * x[1] + 25 * (pow(sin(x[0]), 2) + pow(sin(x[1]), 2));
+    case ORC_FN_SCHAFFER01: {
+        double u = x[0] * x[0] + x[1] * x[1];
+        return 0.5 + (pow(sin(u), 2) - 0.5) / pow(1 + 0.001 * u, 2);
+    }
+    case ORC_FN_DROP_WAVE: {
+        double nx = x[0] * x[0] + x[1] * x[1];
+        return -(1 + cos(12 * sqrt(nx))) / (0.5 * nx + 2);
+    }
+    case ORC_FN_THREE_HUMP_CAMEL:
+        return 2.0 * x[0] * x[0] - 1.05 * pow(x[0], 4.0) + pow(x[0], 6) / 6.0 + x[0] * x[1] + x[1] * x[1];
+    case ORC_FN_ZETTL:
+        return pow(x[0] * x[0] + x[1] * x[1] - 2 * x[0], 2) + 0.25 * x[0];
+    case ORC_FN_LEON:
+        return 100. * pow(x[1] - x[0] * x[0], 2.0) + pow(1 - x[0], 2.0);
+    case ORC_FN_CUBE:
+        return 100.0 * pow(x[1] - pow(x[0], 3.0), 2.0) + pow(1.0 - x[0], 2.0);
+    case ORC_FN_BRENT:
+        return pow(x[0] + 10.0, 2.0) + pow(x[1] + 10.0, 2.0) + exp(-x[0] * x[0] - x[1] * x[1]);
+    case ORC_FN_PRICE01:
+        return pow(fabs(x[0]) - 5.0, 2.0) + pow(fabs(x[1]) - 5.0, 2.0);
+    case ORC_FN_BIRD:
+        return sin(x[0]) * exp(pow(1 - cos(x[1]), 2)) + cos(x[1]) * exp(pow(1 - sin(x[0]), 2)) +
+               pow(x[0] - x[1], 2);
+    case ORC_FN_ACKLEY02:
+        return -200 * exp(-0.02 * sqrt(x[0] * x[0] + x[1] * x[1]));
+    case ORC_FN_ACKLEY03:
+        return -200 * exp(-0.02 * sqrt(x[0] * x[0] + x[1] * x[1])) + 5 * exp(cos(3 * x[0]) + sin(3 * x[1]));
+    case ORC_FN_ZIRILLI:
+        return 0.25 * pow(x[0], 4) - 0.5 * x[0] * x[0] + 0.1 * x[0] + 0.5 * x[1] * x[1];
+    case ORC_FN_ADJIMAN:
+        return cos(x[0]) * sin(x[1]) - x[0] / (x[1] * x[1] + 1);
     default:
         return NAN;
     }

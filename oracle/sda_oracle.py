@@ -15,6 +15,7 @@ _LIB = None
 # functor ids, identical to include/sdaopt_b200.h
 FN = dict(Rastrigin=0, ShiftedRastrigin=1, Rosenbrock=2, Ackley01=3, Schwefel01=4, Schwefel26=5,
           Exponential=6, SuttonChen=7, Constant=8, Sphere=9, Griewank=10)
+FN.update({'Alpine01': 11, 'Brown': 12, 'Cigar': 13, 'CosineMixture': 14, 'Deb01': 15, 'DixonPrice': 16, 'Easom': 17, 'Qing': 18, 'Quintic': 19, 'Salomon': 20, 'Schwefel20': 21, 'Schwefel21': 22, 'Schwefel22': 23, 'Step': 24, 'StyblinskiTang': 25, 'Trid': 26, 'Zacharov': 27, 'SixHumpCamel': 28, 'Beale': 29, 'HimmelBlau': 30, 'Matyas': 31, 'McCormick': 32, 'GoldsteinPrice': 33, 'Levy13': 34, 'Bohachevsky1': 35, 'Bukin06': 36, 'EggCrate': 37, 'Schaffer01': 38, 'DropWave': 39, 'ThreeHumpCamel': 40, 'Zettl': 41, 'Leon': 42, 'Cube': 43, 'Brent': 44, 'Price01': 45, 'Bird': 46, 'Ackley02': 47, 'Ackley03': 48, 'Zirilli': 49, 'Wavy': 50, 'Step2': 51, 'Plateau': 52, 'Sodp': 53, 'Trigonometric02': 54, 'XinSheYang02': 55, 'SineEnvelope': 56, 'Pathological': 57, 'Rana': 58, 'Adjiman': 59})
 RNG_PHILOX, RNG_TAPE = 0, 1
 DEC_IMPROVE, DEC_NEW_BEST, DEC_METRO_ACCEPT, DEC_REJECT = 1, 2, 3, 4
 

@@ -432,7 +432,8 @@ static int cuda_fail(cudaError_t e, const char *what)
 
 static const char *kFunctorNames[SDA_FN_COUNT] = {
     "Rastrigin", "ShiftedRastrigin", "Rosenbrock", "Ackley01", "Schwefel01", "Schwefel26",
-    "Exponential", "SuttonChen", "Constant", "Sphere", "Griewank"};
+    "Exponential", "SuttonChen", "Constant", "Sphere", "Griewank",
+    "Alpine01", "Brown", "Cigar", "CosineMixture", "Deb01", "DixonPrice", "Easom", "Qing", "Quintic", "Salomon", "Schwefel20", "Schwefel21", "Schwefel22", "Step", "StyblinskiTang", "Trid", "Zacharov", "SixHumpCamel", "Beale", "HimmelBlau", "Matyas", "McCormick", "GoldsteinPrice", "Levy13", "Bohachevsky1", "Bukin06", "EggCrate", "Schaffer01", "DropWave", "ThreeHumpCamel", "Zettl", "Leon", "Cube", "Brent", "Price01", "Bird", "Ackley02", "Ackley03", "Zirilli", "Wavy", "Step2", "Plateau", "Sodp", "Trigonometric02", "XinSheYang02", "SineEnvelope", "Pathological", "Rana", "Adjiman"};
 
 extern "C" int sda_abi_version(void) { return SDA_ABI_VERSION; }
 

@@ -102,6 +102,149 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
             b *= cos(v / sqrt((double)(k + 1)));
         }
         return group_sum(a, g) - group_prod(b, g) + 1.0;
+
+    // ---- catalogue widening; formulas: go_benchmark_functions/go_funcs_<initial>.py
+    // n-D forms: lane `lane` of the group takes terms lane, lane+G, ...
+    case SDA_FN_ALPINE01:  // sum |x sin x + 0.1 x|
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double v = x[k]; a += fabs(v * sin(v) + 0.1 * v); }
+        return group_sum(a, g);
+    case SDA_FN_BROWN:  // sum (x_i^2)^(x_{i+1}^2+1) + (x_{i+1}^2)^(x_i^2+1)
+        for (int k = lane; k + 1 < dim; k += SDA_STRIDE) {
+            const double p0 = x[k] * x[k], p1 = x[k + 1] * x[k + 1];
+            a += pow(p0, p1 + 1.0) + pow(p1, p0 + 1.0);
+        }
+        return group_sum(a, g);
+    case SDA_FN_CIGAR:  // x_0^2 + 1e6 sum_{i>=1} x_i^2
+        for (int k = lane; k < dim; k += SDA_STRIDE) { if (k > 0) a += x[k] * x[k]; }
+        return x[0] * x[0] + 1e6 * group_sum(a, g);
+    case SDA_FN_COSINE_MIXTURE:  // -0.1 sum cos(5 pi x) - sum x^2
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double v = x[k]; a += cos(5.0 * kPi * v); b += v * v; }
+        return -0.1 * group_sum(a, g) - group_sum(b, g);
+    case SDA_FN_DEB01:  // -(1/N) sum sin(5 pi x)^6
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double t = sin(5 * kPi * x[k]); const double t2 = t * t; a += t2 * t2 * t2; }
+        return -(1.0 / dim) * group_sum(a, g);
+    case SDA_FN_DIXON_PRICE:  // sum_{i=2..N} i (2 x_i^2 - x_{i-1})^2 + (x_1 - 1)^2
+        for (int k = lane; k + 1 < dim; k += SDA_STRIDE) { const double t = 2.0 * x[k + 1] * x[k + 1] - x[k]; a += (double)(k + 2) * (t * t); }
+        return group_sum(a, g) + (x[0] - 1.0) * (x[0] - 1.0);
+    case SDA_FN_QING:  // sum (x_i^2 - i)^2
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double t = x[k] * x[k] - (double)(k + 1); a += t * t; }
+        return group_sum(a, g);
+    case SDA_FN_QUINTIC:  // sum |x^5 - 3x^4 + 4x^3 + 2x^2 - 10x - 4|
+        for (int k = lane; k < dim; k += SDA_STRIDE) {
+            const double v = x[k], v2 = v * v, v3 = v2 * v, v4 = v2 * v2, v5 = v4 * v;
+            a += fabs(v5 - 3 * v4 + 4 * v3 + 2 * v2 - 10 * v - 4);
+        }
+        return group_sum(a, g);
+    case SDA_FN_SALOMON: {  // 1 - cos(2 pi u) + 0.1 u, u = |x|
+        for (int k = lane; k < dim; k += SDA_STRIDE) a += x[k] * x[k];
+        const double u = sqrt(group_sum(a, g));
+        return 1 - cos(kTwoPi * u) + 0.1 * u;
+    }
+    case SDA_FN_SCHWEFEL20:
+        for (int k = lane; k < dim; k += SDA_STRIDE) a += fabs(x[k]);
+        return group_sum(a, g);
+    case SDA_FN_SCHWEFEL21:
+        for (int k = lane; k < dim; k += SDA_STRIDE) a = fmax(a, fabs(x[k]));
+        for (int o = g.G >> 1; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(g.mask, a, o));
+        return a;
+    case SDA_FN_SCHWEFEL22:
+        b = 1.0;
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double v = fabs(x[k]); a += v; b *= v; }
+        return group_sum(a, g) + group_prod(b, g);
+    case SDA_FN_STEP:
+        for (int k = lane; k < dim; k += SDA_STRIDE) a += floor(fabs(x[k]));
+        return group_sum(a, g);
+    case SDA_FN_STYBLINSKI_TANG:  // sum(x^4 - 16 x^2 + 5 x) / 2
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double v = x[k], v2 = v * v; a += v2 * v2 - 16 * v2 + 5 * v; }
+        return group_sum(a, g) / 2;
+    case SDA_FN_TRID:  // sum (x-1)^2 - sum x_i x_{i-1}
+        for (int k = lane; k < dim; k += SDA_STRIDE) {
+            const double t = x[k] - 1.0;
+            a += t * t;
+            if (k > 0) b += x[k] * x[k - 1];
+        }
+        return group_sum(a, g) - group_sum(b, g);
+    case SDA_FN_ZACHAROV: {  // u + (v/2)^2 + (v/2)^4
+        for (int k = lane; k < dim; k += SDA_STRIDE) { a += x[k] * x[k]; b += (double)(k + 1) * x[k]; }
+        const double u = group_sum(a, g), h = 0.5 * group_sum(b, g), h2 = h * h;
+        return u + h2 + h2 * h2;
+    }
+    case SDA_FN_WAVY:  // 1 - (1/N) sum cos(10x) exp(-x^2/2)
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double v = x[k]; a += cos(10 * v) * exp(-(v * v) / 2.0); }
+        return 1.0 - (1.0 / dim) * group_sum(a, g);
+    case SDA_FN_STEP2:  // sum (floor(x) + 0.5)^2
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double t = floor(x[k]) + 0.5; a += t * t; }
+        return group_sum(a, g);
+    case SDA_FN_PLATEAU:
+        for (int k = lane; k < dim; k += SDA_STRIDE) a += floor(fabs(x[k]));
+        return 30.0 + group_sum(a, g);
+    case SDA_FN_SODP:  // sum |x_i|^(i+1)
+        for (int k = lane; k < dim; k += SDA_STRIDE) a += pow(fabs(x[k]), (double)(k + 2));
+        return group_sum(a, g);
+    case SDA_FN_TRIGONOMETRIC02:  // 1 + sum 8 sin^2(7 t) + 6 sin^2(14 t) + t, t = (x-0.9)^2
+        for (int k = lane; k < dim; k += SDA_STRIDE) {
+            const double d = x[k] - 0.9, t = d * d, s7 = sin(7 * t), s14 = sin(14 * t);
+            a += 8 * (s7 * s7) + 6 * (s14 * s14) + t;
+        }
+        return 1.0 + group_sum(a, g);
+    case SDA_FN_XIN_SHE_YANG02:  // sum|x| exp(-sum sin(x^2))
+        for (int k = lane; k < dim; k += SDA_STRIDE) { const double v = x[k]; a += fabs(v); b += sin(v * v); }
+        return group_sum(a, g) * exp(-group_sum(b, g));
+    case SDA_FN_SINE_ENVELOPE:  // sum (sin^2(sqrt(q)) - 0.5) / (1 + 0.001 q)^2 + 0.5, q = x_i^2 + x_{i+1}^2
+        for (int k = lane; k + 1 < dim; k += SDA_STRIDE) {
+            const double q = x[k] * x[k] + x[k + 1] * x[k + 1], sn = sin(sqrt(q)), dn = 1 + 0.001 * q;
+            a += (sn * sn - 0.5) / (dn * dn) + 0.5;
+        }
+        return group_sum(a, g);
+    case SDA_FN_PATHOLOGICAL:
+        for (int k = lane; k + 1 < dim; k += SDA_STRIDE) {
+            const double p0 = x[k], p1 = x[k + 1], sn = sin(sqrt(100 * (p0 * p0) + p1 * p1));
+            const double q = p0 * p0 - 2 * p0 * p1 + p1 * p1;
+            a += 0.5 + (sn * sn - 0.5) / (1. + 0.001 * (q * q));
+        }
+        return group_sum(a, g);
+    case SDA_FN_RANA:
+        for (int k = lane; k + 1 < dim; k += SDA_STRIDE) {
+            const double p0 = x[k], p1 = x[k + 1];
+            const double t1 = sqrt(fabs(p1 + p0 + 1)), t2 = sqrt(fabs(p1 - p0 + 1));
+            a += (p1 + 1) * cos(t2) * sin(t1) + p0 * cos(t1) * sin(t2);
+        }
+        return group_sum(a, g);
+    // fixed 2-D forms: every lane evaluates the expression (no reduction)
+    case SDA_FN_EASOM: { const double p = x[0], q = x[1]; const double e = (p - kPi) * (p - kPi) + (q - kPi) * (q - kPi); return -cos(p) * cos(q) * exp(-e); }
+    case SDA_FN_SIX_HUMP_CAMEL: { const double p = x[0], q = x[1], p2 = p * p, q2 = q * q; return (4 - 2.1 * p2 + p2 * p2 / 3) * p2 + p * q + (4 * q2 - 4) * q2; }
+    case SDA_FN_BEALE: { const double p = x[0], q = x[1]; const double t1 = 1.5 - p + p * q, t2 = 2.25 - p + p * (q * q), t3 = 2.625 - p + p * (q * q * q); return t1 * t1 + t2 * t2 + t3 * t3; }
+    case SDA_FN_HIMMEL_BLAU: { const double p = x[0], q = x[1]; const double t1 = p * p + q - 11, t2 = p + q * q - 7; return t1 * t1 + t2 * t2; }
+    case SDA_FN_MATYAS: { const double p = x[0], q = x[1]; return 0.26 * (p * p + q * q) - 0.48 * p * q; }
+    case SDA_FN_MC_CORMICK: { const double p = x[0], q = x[1]; return sin(p + q) + (p - q) * (p - q) - 1.5 * p + 2.5 * q + 1; }
+    case SDA_FN_GOLDSTEIN_PRICE: {
+        const double p = x[0], q = x[1];
+        const double s1 = p + q + 1, s2 = 2 * p - 3 * q;
+        const double t1 = 1 + s1 * s1 * (19 - 14 * p + 3 * (p * p) - 14 * q + 6 * p * q + 3 * (q * q));
+        const double t2 = 30 + s2 * s2 * (18 - 32 * p + 12 * (p * p) + 48 * q - 36 * p * q + 27 * (q * q));
+        return t1 * t2;
+    }
+    case SDA_FN_LEVY13: {
+        const double p = x[0], q = x[1];
+        const double s3p = sin(3 * kPi * p), s3q = sin(3 * kPi * q), s2q = sin(kTwoPi * q);
+        return s3p * s3p + (p - 1) * (p - 1) * (1 + s3q * s3q) + (q - 1) * (q - 1) * (1 + s2q * s2q);
+    }
+    case SDA_FN_BOHACHEVSKY1: { const double p = x[0], q = x[1]; return p * p + 2 * (q * q) - 0.3 * cos(3 * kPi * p) - 0.4 * cos(4 * kPi * q) + 0.7; }
+    case SDA_FN_BUKIN06: { const double p = x[0], q = x[1]; return 100 * sqrt(fabs(q - 0.01 * (p * p))) + 0.01 * fabs(p + 10); }
+    case SDA_FN_EGG_CRATE: { const double p = x[0], q = x[1], sp = sin(p), sq = sin(q); return p * p + q * q + 25 * (sp * sp + sq * sq); }
+    case SDA_FN_SCHAFFER01: { const double u = x[0] * x[0] + x[1] * x[1], sn = sin(u), dn = 1 + 0.001 * u; return 0.5 + (sn * sn - 0.5) / (dn * dn); }
+    case SDA_FN_DROP_WAVE: { const double nx = x[0] * x[0] + x[1] * x[1]; return -(1 + cos(12 * sqrt(nx))) / (0.5 * nx + 2); }
+    case SDA_FN_THREE_HUMP_CAMEL: { const double p = x[0], q = x[1], p2 = p * p; return 2.0 * p2 - 1.05 * (p2 * p2) + (p2 * p2 * p2) / 6.0 + p * q + q * q; }
+    case SDA_FN_ZETTL: { const double p = x[0], q = x[1]; const double t = p * p + q * q - 2 * p; return t * t + 0.25 * p; }
+    case SDA_FN_LEON: { const double p = x[0], q = x[1]; const double t = q - p * p; return 100. * (t * t) + (1 - p) * (1 - p); }
+    case SDA_FN_CUBE: { const double p = x[0], q = x[1]; const double t = q - p * p * p; return 100.0 * (t * t) + (1.0 - p) * (1.0 - p); }
+    case SDA_FN_BRENT: { const double p = x[0], q = x[1]; return (p + 10.0) * (p + 10.0) + (q + 10.0) * (q + 10.0) + exp(-(p * p) - q * q); }
+    case SDA_FN_PRICE01: { const double t1 = fabs(x[0]) - 5.0, t2 = fabs(x[1]) - 5.0; return t1 * t1 + t2 * t2; }
+    case SDA_FN_BIRD: { const double p = x[0], q = x[1], c1 = 1 - cos(q), c2 = 1 - sin(p); return sin(p) * exp(c1 * c1) + cos(q) * exp(c2 * c2) + (p - q) * (p - q); }
+    case SDA_FN_ACKLEY02: return -200 * exp(-0.02 * sqrt(x[0] * x[0] + x[1] * x[1]));
+    case SDA_FN_ACKLEY03: { const double p = x[0], q = x[1]; return -200 * exp(-0.02 * sqrt(p * p + q * q)) + 5 * exp(cos(3 * p) + sin(3 * q)); }
+    case SDA_FN_ZIRILLI: { const double p = x[0], q = x[1], p2 = p * p; return 0.25 * (p2 * p2) - 0.5 * p2 + 0.1 * p + 0.5 * (q * q); }
+    case SDA_FN_ADJIMAN: { const double p = x[0], q = x[1]; return cos(p) * sin(q) - p / (q * q + 1); }
     default:
         return __longlong_as_double(0x7ff8000000000000LL);
     }

@@ -21,6 +21,112 @@ from . import _lib
 FUNCTOR_IDS = dict(Rastrigin=0, ShiftedRastrigin=1, Rosenbrock=2, Ackley01=3, Schwefel01=4,
                    Schwefel26=5, Exponential=6, SuttonChen=7, Constant=8, Sphere=9, Griewank=10)
 
+FUNCTOR_IDS.update({
+    'Alpine01': 11,
+    'Brown': 12,
+    'Cigar': 13,
+    'CosineMixture': 14,
+    'Deb01': 15,
+    'DixonPrice': 16,
+    'Easom': 17,
+    'Qing': 18,
+    'Quintic': 19,
+    'Salomon': 20,
+    'Schwefel20': 21,
+    'Schwefel21': 22,
+    'Schwefel22': 23,
+    'Step': 24,
+    'StyblinskiTang': 25,
+    'Trid': 26,
+    'Zacharov': 27,
+    'SixHumpCamel': 28,
+    'Beale': 29,
+    'HimmelBlau': 30,
+    'Matyas': 31,
+    'McCormick': 32,
+    'GoldsteinPrice': 33,
+    'Levy13': 34,
+    'Bohachevsky1': 35,
+    'Bukin06': 36,
+    'EggCrate': 37,
+    'Schaffer01': 38,
+    'DropWave': 39,
+    'ThreeHumpCamel': 40,
+    'Zettl': 41,
+    'Leon': 42,
+    'Cube': 43,
+    'Brent': 44,
+    'Price01': 45,
+    'Bird': 46,
+    'Ackley02': 47,
+    'Ackley03': 48,
+    'Zirilli': 49,
+    'Wavy': 50,
+    'Step2': 51,
+    'Plateau': 52,
+    'Sodp': 53,
+    'Trigonometric02': 54,
+    'XinSheYang02': 55,
+    'SineEnvelope': 56,
+    'Pathological': 57,
+    'Rana': 58,
+    'Adjiman': 59,
+})
+
+# name: (default N, n-D capable, box or per-dimension bounds, fglob or fglob(N)) -- the class
+# attributes of go_benchmark_functions/go_funcs_*.py (`_bounds`, `fglob`, `change_dimensionality`)
+_CATALOGUE2 = {
+    'Alpine01': (2, True, (-10.0, 10.0), 0.0),
+    'Brown': (2, True, (-1.0, 4.0), 0.0),
+    'Cigar': (2, True, (-100.0, 100.0), 0.0),
+    'CosineMixture': (2, True, (-1.0, 1.0), lambda n: -0.9 * n),
+    'Deb01': (2, True, (-1.0, 1.0), -1.0),
+    'DixonPrice': (2, True, (-10.0, 10.0), 0.0),
+    'Easom': (2, False, (-100.0, 100.0), -1.0),
+    'Qing': (2, True, (-500.0, 500.0), 0.0),
+    'Quintic': (2, True, (-10.0, 10.0), 0.0),
+    'Salomon': (2, True, (-100.0, 100.0), 0.0),
+    'Schwefel20': (2, True, (-100.0, 100.0), 0.0),
+    'Schwefel21': (2, True, (-100.0, 100.0), 0.0),
+    'Schwefel22': (2, True, (-100.0, 100.0), 0.0),
+    'Step': (2, True, (-100.0, 100.0), 0.0),
+    'StyblinskiTang': (2, True, (-5.0, 5.0), lambda n: -39.16616570377142 * n),
+    'Trid': (6, True, (-20.0, 20.0), -50.0),
+    'Zacharov': (2, True, (-5.0, 10.0), 0.0),
+    'SixHumpCamel': (2, False, (-5.0, 5.0), -1.031628),
+    'Beale': (2, False, (-4.5, 4.5), 0.0),
+    'HimmelBlau': (2, False, (-5.0, 5.0), 0.0),
+    'Matyas': (2, False, (-10.0, 10.0), 0.0),
+    'McCormick': (2, False, [(-1.5, 4.0), (-3.0, 3.0)], -1.913222954981037),
+    'GoldsteinPrice': (2, False, (-2.0, 2.0), 3.0),
+    'Levy13': (2, False, (-10.0, 10.0), 0.0),
+    'Bohachevsky1': (2, False, (-100.0, 100.0), 0.0),
+    'Bukin06': (2, False, [(-15.0, -5.0), (-3.0, 3.0)], 0.0),
+    'EggCrate': (2, False, (-5.0, 5.0), 0.0),
+    'Schaffer01': (2, False, (-100.0, 100.0), 0.0),
+    'DropWave': (2, False, (-5.12, 5.12), -1.0),
+    'ThreeHumpCamel': (2, False, (-5.0, 5.0), 0.0),
+    'Zettl': (2, False, (-5.0, 10.0), -0.003791237220468656),
+    'Leon': (2, False, (-1.2, 1.2), 0.0),
+    'Cube': (2, False, (-10.0, 10.0), 0.0),
+    'Brent': (2, False, (-10.0, 10.0), 0.0),
+    'Price01': (2, False, (-500.0, 500.0), 0.0),
+    'Bird': (2, False, (-6.283185307179586, 6.283185307179586), -106.7645367198034),
+    'Ackley02': (2, False, (-32.0, 32.0), -200.0),
+    'Ackley03': (2, False, (-32.0, 32.0), -195.6290282592388),
+    'Zirilli': (2, False, (-10.0, 10.0), -0.35238603),
+    'Wavy': (2, True, (-3.141592653589793, 3.141592653589793), 0.0),
+    'Step2': (2, True, (-100.0, 100.0), 0.5),
+    'Plateau': (2, True, (-5.12, 5.12), 30.0),
+    'Sodp': (2, True, (-1.0, 1.0), 0.0),
+    'Trigonometric02': (2, True, (-500.0, 500.0), 1.0),
+    'XinSheYang02': (2, True, (-6.283185307179586, 6.283185307179586), 0.0),
+    'SineEnvelope': (2, True, (-100.0, 100.0), 0.0),
+    'Pathological': (2, False, (-100.0, 100.0), 0.0),
+    'Rana': (2, True, (-500.000001, 500.000001), -500.8021602966615),
+    'Adjiman': (2, False, [(-1.0, 2.0), (-1.0, 1.0)], -2.02180678),
+}
+
 # default box and known optimum of the catalogue classes (go_funcs_*.py `__init__`)
 _CATALOGUE = {
     "Rastrigin": ((-5.12, 5.12), 0.0),      # go_funcs_R.py:80-86
@@ -45,6 +151,12 @@ class DeviceFunctor(object):
         self.params = np.ascontiguousarray(params, dtype=np.float64).ravel()
         self.N = dimensions
         box, fglob = _CATALOGUE.get(name, (None, float("nan")))
+        if name in _CATALOGUE2:
+            n_default, _, box, fglob = _CATALOGUE2[name]
+            if self.N is None:
+                self.N = n_default
+            if callable(fglob):
+                fglob = fglob(self.N)
         self.fglob = fglob
         self._box = box
 
@@ -52,6 +164,8 @@ class DeviceFunctor(object):
     def bounds(self):
         if self._box is None or self.N is None:
             raise AttributeError("%s has no default bounds" % self.name)
+        if isinstance(self._box, list):                    # per-dimension bounds (fixed-N classes)
+            return list(self._box)
         return [self._box] * int(self.N)
 
     def fun(self, x, *args):

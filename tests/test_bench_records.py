@@ -84,5 +84,7 @@ def test_job_list_follows_reference_rules():
     assert names[:12] == ['Ackley01_5', 'Ackley01_10', 'Ackley01_20', 'Ackley01_30', 'Ackley01_40',
                           'Ackley01_50', 'Ackley01_60', 'Ackley01_70', 'Ackley01_80', 'Ackley01_90',
                           'Ackley01_100', 'Ackley01']
-    assert len(jobs) == 8 + 5 * 11
+    from sdaopt_b200 import functors
+    assert len(jobs) == 8 + len(functors._CATALOGUE2) + 5 * 11
+    assert ('Trid', 'Trid', 6) in jobs and ('McCormick', 'McCormick', 2) in jobs
     assert ('Griewank', 'Griewank', 2) in jobs and not any(n.startswith('Griewank_') for n in names)
