@@ -108,7 +108,13 @@ enum {
     SDA_FN_PATHOLOGICAL = 57,
     SDA_FN_RANA = 58,
     SDA_FN_ADJIMAN = 59,
-    SDA_FN_COUNT
+    SDA_FN_COUNT,
+    /* user-supplied CUDA device functor (north star; replaces an arbitrary Python `func`,
+     * _sda.py:440-444).  Available only in a library built with -DSDA_USER_FUNCTOR_HEADER="<file>"
+     * where <file> defines
+     *   template <class X> __device__ double sda_user_objective(const X &x, int dim, const double *params);
+     * (x[k] is the k-th coordinate).  sdaopt_b200.functors.compile_user_functor() does the build. */
+    SDA_FN_USER = 255
 };
 
 enum { SDA_RNG_PHILOX = 0, SDA_RNG_TAPE = 1 };
@@ -182,6 +188,8 @@ const char *sda_last_cuda_error(void);
 /* functor id for a registered name ("Rastrigin", ...), or SDA_E_INVALID */
 int sda_functor_id(const char *name);
 const char *sda_functor_name(int functor);
+/* 1 if this build contains a user functor (SDA_FN_USER), else 0 */
+int sda_has_user_functor(void);
 /* number of CUDA devices visible, or SDA_E_CUDA */
 int sda_device_count(void);
 

@@ -15,7 +15,7 @@ RNG_PHILOX, RNG_TAPE = 0, 1
 CHAIN_REINIT_FAILED, CHAIN_TAPE_EXHAUSTED = 1, 2
 
 # every symbol include/sdaopt_b200.h declares
-EXPORTS = ["sda_abi_version", "sda_error_string", "sda_last_cuda_error", "sda_functor_id",
+EXPORTS = ["sda_abi_version", "sda_has_user_functor", "sda_error_string", "sda_last_cuda_error", "sda_functor_id",
            "sda_functor_name", "sda_device_count", "sda_workspace_bytes", "sda_batch_run",
            "sda_batch_run_host", "sda_eval", "sda_eval_host", "sda_visiting_host",
            "sda_visit_fn_host", "sda_local_search_host", "sda_fp64_peak"]
@@ -56,18 +56,20 @@ class SdaError(RuntimeError):
         super().__init__(msg + (" " + detail if detail else ""))
 
 
-_LIB = None
+_LIBS = {}
+SDA_FN_USER = 255
 
 
-def lib():
-    """The loaded CUDA library.  Raises if it was not built (python -m sdaopt_b200.build)."""
-    global _LIB
-    if _LIB is None:
-        if not os.path.exists(LIB_PATH):
+def lib(path=None):
+    """The loaded CUDA library (default build, or the build that carries a user functor).
+    Raises if it was not built (python -m sdaopt_b200.build)."""
+    path = path or LIB_PATH
+    if path not in _LIBS:
+        if not os.path.exists(path):
             raise ImportError(
-                "libsdaopt_b200.so is missing: build it with `python -m sdaopt_b200.build` "
-                "(needs nvcc); sdaopt_b200 has no CPU fallback")
-        L = C.CDLL(LIB_PATH)
+                "%s is missing: build it with `python -m sdaopt_b200.build` "
+                "(needs nvcc); sdaopt_b200 has no CPU fallback" % path)
+        L = C.CDLL(path)
         L.sda_abi_version.restype = C.c_int
         L.sda_error_string.restype = C.c_char_p
         L.sda_error_string.argtypes = [C.c_int]
@@ -103,10 +105,11 @@ def lib():
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.sda_fp64_peak.restype = C.c_int
         L.sda_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+        L.sda_has_user_functor.restype = C.c_int
         if L.sda_abi_version() != 1:
             raise ImportError("libsdaopt_b200.so ABI mismatch")
-        _LIB = L
-    return _LIB
+        _LIBS[path] = L
+    return _LIBS[path]
 
 
 def check(rc, detail=""):

@@ -131,7 +131,7 @@ def sda_batch(func, bounds, n_chains, x0=None, seeds=None, tape=None, maxiter=10
         f_hit=np.zeros(n_chains), trace_e=np.zeros((n_chains, max(tl, 1))),
         trace_d=np.zeros((n_chains, max(tl, 1)), np.uint8), tape_used=np.zeros(n_chains, np.int64))
     res = _lib.SdaResult(*[out[k].ctypes.data for k in _lib.RESULT_FIELDS])
-    rc = _lib.lib().sda_batch_run_host(C.byref(problem), C.byref(cfg), n_chains, _ptr(x0),
+    rc = _lib.lib(functor.library_path).sda_batch_run_host(C.byref(problem), C.byref(cfg), n_chains, _ptr(x0),
                                        _ptr(seeds), _ptr(tape), tape_len, C.byref(res), int(device))
     _lib.check(rc)
     out["trace_e"] = out["trace_e"][:, :tl]
@@ -268,7 +268,7 @@ class ObjectiveFunWrapper(object):
         ok = np.zeros(1, np.int32)
         nfev = np.zeros(1, np.int64)
         _lib.require_cuda()
-        _lib.check(_lib.lib().sda_local_search_host(C.byref(problem), x.ctypes.data, 1,
+        _lib.check(_lib.lib(self.func.library_path).sda_local_search_host(C.byref(problem), x.ctypes.data, 1,
                                                      xo.ctypes.data, fo.ctypes.data, ok.ctypes.data,
                                                      nfev.ctypes.data, device))
         self.nb_fun_call += int(nfev[0])

@@ -47,5 +47,13 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_user(header_path, out_path):
+    """The same library with a user-supplied device functor compiled in as SDA_FN_USER."""
+    cmd = [_nvcc()] + NVCC_FLAGS + ['-DSDA_USER_FUNCTOR_HEADER="%s"' % os.path.abspath(header_path),
+                                    "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return out_path
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

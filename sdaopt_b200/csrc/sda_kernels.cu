@@ -437,6 +437,21 @@ static const char *kFunctorNames[SDA_FN_COUNT] = {
 
 extern "C" int sda_abi_version(void) { return SDA_ABI_VERSION; }
 
+extern "C" int sda_has_user_functor(void)
+{
+#ifdef SDA_USER_FUNCTOR_HEADER
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+static bool functor_ok(int f)
+{
+    if (f >= 0 && f < SDA_FN_COUNT) return true;
+    return f == SDA_FN_USER && sda_has_user_functor();
+}
+
 extern "C" const char *sda_error_string(int code)
 {
     switch (code) {
@@ -523,6 +538,15 @@ static int pick_group(int dim, int rng_mode)
     return g;
 }
 
+// a user functor is evaluated whole by every lane of its group, so fewer lanes per chain waste
+// less: the smallest G whose 32/G chain rows (3*D doubles each) still fit 16 KB per warp
+static int pick_group_user(int dim)
+{
+    int g = 1;
+    while (g < 32 && (size_t)(32 / g) * 3 * dim * sizeof(double) > 16384) g <<= 1;
+    return g;
+}
+
 struct LaunchPlan {
     int warps_per_block, blocks, group;
     size_t smem;
@@ -599,7 +623,7 @@ extern "C" size_t sda_workspace_bytes(const SdaProblem *p, const SdaConfig *c, i
 static int validate(const SdaProblem *p, const SdaConfig *c, int64_t n_chains)
 {
     if (!p || !c || p->dim <= 0 || n_chains <= 0) return SDA_E_INVALID;
-    if (p->functor < 0 || p->functor >= SDA_FN_COUNT) return SDA_E_INVALID;
+    if (!functor_ok(p->functor)) return SDA_E_INVALID;
     if (c->rng_mode != SDA_RNG_PHILOX && c->rng_mode != SDA_RNG_TAPE) return SDA_E_INVALID;
     if (p->functor == SDA_FN_SUTTON_CHEN && p->dim % 3 != 0) return SDA_E_INVALID;
     if ((p->functor == SDA_FN_SHIFTED_RASTRIGIN || p->functor == SDA_FN_CONSTANT) &&
@@ -620,7 +644,9 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     if (c->rng_mode == SDA_RNG_TAPE && (!tape || tape_len <= 0)) return SDA_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     LaunchPlan lp;
-    rc = plan_launch(p->dim, n_chains, c->pure_sa, pick_group(p->dim, c->rng_mode), &lp);
+    rc = plan_launch(p->dim, n_chains, c->pure_sa,
+                     (p->functor == SDA_FN_USER && c->rng_mode != SDA_RNG_TAPE) ? pick_group_user(p->dim)
+                                                                                : pick_group(p->dim, c->rng_mode), &lp);
     if (rc) return rc;
     size_t off_temp, off_sig, off_xmin, off_ls;
     long long ls_stride;
@@ -760,11 +786,11 @@ extern "C" int sda_batch_run_host(const SdaProblem *p, const SdaConfig *c, int64
 extern "C" int sda_eval(const SdaProblem *p, const double *x, int64_t n, double *f, void *stream)
 {
     if (!p || !x || !f || n <= 0 || p->dim <= 0) return SDA_E_INVALID;
-    if (p->functor < 0 || p->functor >= SDA_FN_COUNT) return SDA_E_INVALID;
+    if (!functor_ok(p->functor)) return SDA_E_INVALID;
     long long blocks = (n + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     sda::sda_eval_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p->functor, p->dim, p->params, x, n, f,
-                                                                       pick_group(p->dim, SDA_RNG_PHILOX));
+                                                                       p->functor == SDA_FN_USER ? pick_group_user(p->dim) : pick_group(p->dim, SDA_RNG_PHILOX));
     CK(cudaGetLastError());
     return SDA_OK;
 }
@@ -836,7 +862,7 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
                                      int device)
 {
     if (!p || !x_in || !x_out || !f_out || n <= 0 || p->dim <= 0) return SDA_E_INVALID;
-    if (p->functor < 0 || p->functor >= SDA_FN_COUNT) return SDA_E_INVALID;
+    if (!functor_ok(p->functor)) return SDA_E_INVALID;
     CK(cudaSetDevice(device));
     DevBuf lo, up, pa, dxi, dxo, dfo, dsu, dnf, dls;
     SdaProblem dp;

@@ -9,6 +9,10 @@
 
 #include "sda_device.cuh"
 
+#ifdef SDA_USER_FUNCTOR_HEADER
+#include SDA_USER_FUNCTOR_HEADER
+#endif
+
 namespace sda {
 
 // suttonchen.py:23-40  (A=1, C=39.432, M=6, K=9).  Lane L owns atoms L, L+32, ...: for each it
@@ -245,6 +249,11 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
     case SDA_FN_ACKLEY03: { const double p = x[0], q = x[1]; return -200 * exp(-0.02 * sqrt(p * p + q * q)) + 5 * exp(cos(3 * p) + sin(3 * q)); }
     case SDA_FN_ZIRILLI: { const double p = x[0], q = x[1], p2 = p * p; return 0.25 * (p2 * p2) - 0.5 * p2 + 0.1 * p + 0.5 * (q * q); }
     case SDA_FN_ADJIMAN: { const double p = x[0], q = x[1]; return cos(p) * sin(q) - p / (q * q + 1); }
+#ifdef SDA_USER_FUNCTOR_HEADER
+    // user-supplied device functor: every lane of the group evaluates it (group-uniform result)
+    case SDA_FN_USER:
+        return ::sda_user_objective(x, dim, params);
+#endif
     default:
         return __longlong_as_double(0x7ff8000000000000LL);
     }

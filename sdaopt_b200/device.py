@@ -54,7 +54,8 @@ class DeviceBatch(object):
             ncall_hit=torch.empty(Cn, dtype=i64, device=dev), f_hit=torch.empty(Cn, dtype=f64, device=dev))
         self.result = _lib.SdaResult(*[self.out[k].data_ptr() if k in self.out else None
                                        for k in _lib.RESULT_FIELDS])
-        nbytes = _lib.lib().sda_workspace_bytes(C.byref(self.problem), C.byref(self.cfg), Cn)
+        self._L = _lib.lib(self.functor.library_path)
+        nbytes = self._L.sda_workspace_bytes(C.byref(self.problem), C.byref(self.cfg), Cn)
         self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         # pinned host mirrors for the end-to-end form
         self.h_seeds = torch.empty(Cn, dtype=i64).pin_memory()
@@ -67,7 +68,7 @@ class DeviceBatch(object):
     def launch(self):
         """One persistent kernel on torch's current stream (asynchronous)."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        rc = _lib.lib().sda_batch_run(
+        rc = self._L.sda_batch_run(
             C.byref(self.problem), C.byref(self.cfg), self.n_chains,
             self.x0.data_ptr() if self.x0 is not None else None, self.seeds.data_ptr(), None, 0,
             C.byref(self.result), self.workspace.data_ptr(), self.workspace.numel(),

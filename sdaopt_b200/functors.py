@@ -12,6 +12,8 @@ evaluates objectives inside the annealing kernel, so ``func`` must name a device
 Anything else raises ``TypeError``: there is no CPU fallback.
 """
 import ctypes as C
+import hashlib
+import os
 
 import numpy as np
 
@@ -159,6 +161,7 @@ class DeviceFunctor(object):
                 fglob = fglob(self.N)
         self.fglob = fglob
         self._box = box
+        self.library_path = None        # set for user functors: the build that contains them
 
     @property
     def bounds(self):
@@ -208,6 +211,39 @@ def Constant(value):
     return DeviceFunctor("Constant", params=[value])
 
 
+def compile_user_functor(source, params=(), name="user", bounds=None, fglob=float("nan"),
+                          build_dir=None):
+    """User-supplied CUDA device functor (replaces the reference's arbitrary Python ``func``,
+    _sda.py:440-444).  ``source`` must define
+
+        template <class X>
+        __device__ double sda_user_objective(const X &x, int dim, const double *params);
+
+    where ``x[k]`` is the k-th coordinate.  The annealing / local-search kernels are rebuilt with
+    the functor inlined (nvcc, about a minute, cached by source hash under build/user/) and the
+    returned DeviceFunctor routes every call to that library.  No CPU evaluation ever happens."""
+    from . import build as _build
+    digest = hashlib.sha1(source.encode()).hexdigest()[:16]
+    root = build_dir or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                     "build", "user", digest)
+    os.makedirs(root, exist_ok=True)
+    header = os.path.join(root, "user_functor.cuh")
+    so = os.path.join(root, "libsdaopt_b200_user.so")
+    if not os.path.exists(so):
+        with open(header, "w") as fh:
+            fh.write("// user functor %s\n#pragma once\n%s\n" % (name, source))
+        _build.build_user(header, so)
+    f = DeviceFunctor.__new__(DeviceFunctor)
+    f.name = name
+    f.functor_id = _lib.SDA_FN_USER
+    f.params = np.ascontiguousarray(params, dtype=np.float64).ravel()
+    f.N = None if bounds is None else len(bounds)
+    f.fglob = fglob
+    f._box = None if bounds is None else [tuple(b) for b in bounds]
+    f.library_path = so
+    return f
+
+
 def resolve(func):
     """Map the reference's ``func`` argument to a DeviceFunctor or raise TypeError."""
     if isinstance(func, DeviceFunctor):
@@ -250,5 +286,6 @@ def evaluate(functor, points, device=0):
     p, keep = make_problem(functor, dummy, dummy + 1)
     out = np.empty(n, dtype=np.float64)
     _lib.require_cuda()
-    _lib.check(_lib.lib().sda_eval_host(C.byref(p), pts.ctypes.data, n, out.ctypes.data, device))
+    _lib.check(_lib.lib(functor.library_path).sda_eval_host(C.byref(p), pts.ctypes.data, n,
+                                                         out.ctypes.data, device))
     return out

@@ -363,3 +363,31 @@ def test_suite_runner_writes_reference_format(sb, oracle, tmp_path):
     assert len(rows) == 14 and rows[0][0] == "Function name"
     # a second run skips existing files (bench.py:164-167)
     assert Benchmarker(20, folder, names=["Rastrigin", "Sphere"], max_calls=100000).run() == []
+
+
+# ---- user-supplied CUDA device functor --------------------------------------------------
+USER_SRC = r"""
+// shifted, scaled Rastrigin written by a "user": params = {shift, amplitude}
+template <class X>
+__device__ double sda_user_objective(const X &x, int dim, const double *params)
+{
+    double s = 0.0;
+    for (int k = 0; k < dim; ++k) {
+        const double d = x[k] - params[0];
+        s += d * d - params[1] * cos(6.283185307179586 * d);
+    }
+    return s + params[1] * dim;
+}
+"""
+
+
+def test_user_cuda_functor(sb):
+    f = sb.functors.compile_user_functor(USER_SRC, params=[0.5, 10.0], name="my_rastrigin")
+    X = np.random.RandomState(3).uniform(-4, 5, (32, 6))
+    want = np.sum((X - 0.5) ** 2 - 10.0 * np.cos(2 * np.pi * (X - 0.5)), axis=1) + 10.0 * 6
+    np.testing.assert_allclose(f(X), want, rtol=1e-12, atol=1e-11)
+    ret = sb.sda(f, None, [(-4.62, 5.62)] * 6, seed=7)
+    assert ret.fun < 1e-10 and np.allclose(ret.x, 0.5, atol=1e-5) and ret.nit == 1000
+    # the default library does not know the functor id
+    from sdaopt_b200 import _lib
+    assert _lib.lib().sda_has_user_functor() == 0 and _lib.lib(f.library_path).sda_has_user_functor() == 1
