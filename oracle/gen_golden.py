@@ -315,6 +315,35 @@ def gen_suite():
     np.savez_compressed(os.path.join(GOLD, "suite_runs.npz"), rows=np.array(rows, dtype=object))
 
 
+def gen_suite_stats():
+    """The north star's statistical criterion needs the REFERENCE's own distribution: NB_RUNS = 100
+    suite-mode runs (bench.py:170-216 semantics, seeds 1234+i) of a few jobs; success / ncall /
+    fvalue arrays as BenchUnit would hold them."""
+    rows = []
+    for name, dim in [("Rastrigin", None), ("Rastrigin", 5), ("Rastrigin", 10), ("Ackley01", None),
+                      ("Ackley01", 10), ("Rosenbrock", None), ("Schwefel01", 5), ("Sphere", None),
+                      ("Easom", None), ("Exponential", 10), ("Beale", None), ("HimmelBlau", None),
+                      ("Zacharov", None), ("StyblinskiTang", None), ("Levy13", None)]:
+        klass = getattr(gbf, name)
+        succ, ncall, fval = [], [], []
+        for i in range(100):
+            algo = refbench.SDAOptimizer()
+            np.random.seed(1234 + i)
+            algo.prepare(name, klass, dim)
+            algo._maxcall = 200000
+            try:
+                algo.optimize()
+            except (refbench.OptimumFoundException, refbench.OptimumNotFoundException):
+                pass
+            succ.append(bool(algo.success)); ncall.append(int(algo.fcall_success)); fval.append(float(algo.fsuccess))
+        k = algo._k
+        rows.append(dict(functor=name, dim=k.N, success=np.array(succ), ncall=np.array(ncall),
+                         fvalue=np.array(fval), fglob=float(k.fglob), max_calls=200000,
+                         bounds=np.array(k.bounds, dtype=float)))
+        print("suite-stats", name, k.N, "success", np.mean(succ), "median ncall", np.median(ncall), flush=True)
+    np.savez_compressed(os.path.join(GOLD, "suite_stats_ref.npz"), rows=np.array(rows, dtype=object))
+
+
 def gen_asrun_summary():
     D = 50
     np.random.seed(1234)
@@ -334,6 +363,8 @@ def gen_asrun_summary():
 if __name__ == "__main__":
     if MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "objectives":
         gen_objective_points()
+    elif MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "suite_stats":
+        gen_suite_stats()
     elif os.environ.get("SDA_GOLDEN_ONLY"):
         pass
     elif MODE == "libm":
@@ -343,5 +374,6 @@ if __name__ == "__main__":
         gen_ls_runs()
         gen_lbfgsb()
         gen_suite()
+        gen_suite_stats()
     else:
         gen_asrun_summary()

@@ -48,12 +48,13 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
     const int lane = g.gl, SDA_STRIDE = g.G;
     double a = 0.0, b = 0.0;
     switch (fid) {
-    case SDA_FN_RASTRIGIN:  // go_funcs_R.py:91   10*N + sum(x^2 - 10 cos(2 pi x))
+    case SDA_FN_RASTRIGIN: {  // go_funcs_R.py:91   10*N + sum(x^2 - 10 cos(2 pi x))
         for (int k = lane; k < dim; k += SDA_STRIDE) {
             const double v = x[k];
             a += v * v - 10.0 * cos(kTwoPi * v);
         }
         return 10.0 * dim + group_sum(a, g);
+    }
     case SDA_FN_SHIFTED_RASTRIGIN: {  // README.md:65-66
         const double shift = params[0];
         for (int k = lane; k < dim; k += SDA_STRIDE) {

@@ -391,3 +391,30 @@ def test_user_cuda_functor(sb):
     # the default library does not know the functor id
     from sdaopt_b200 import _lib
     assert _lib.lib().sda_has_user_functor() == 0 and _lib.lib(f.library_path).sda_has_user_functor() == 1
+
+
+# ---- the north star's statistical criterion against the REFERENCE's own runs ---------------------------
+def test_suite_statistics_match_reference(sb):
+    """tests/golden/suite_stats_ref.npz holds NB_RUNS = 100 suite-mode runs of the live reference
+    (seeds 1234+i, bench.py:170-216) for 15 jobs.  The GPU runs use Philox keys, so the two samples
+    are independent draws: success rate inside the reference's Wilson 95 % interval, median
+    ncall-to-global inside the reference's order-statistic interval (99.9 % ranks 34..67 of 100, the
+    95 % ranks 40..61 are reported), and a two-sided Mann-Whitney test that does not reject at 1e-3."""
+    from scipy.stats import mannwhitneyu
+    rows = load_golden("suite_stats_ref.npz")["rows"]
+    inside95 = 0
+    for r in rows:
+        f = sb.DeviceFunctor(r["functor"], dimensions=r["dim"])
+        n = 100
+        seeds = np.arange(n, dtype=np.uint64) + np.uint64(1234)
+        g = sb.sda_batch(f, r["bounds"], n, seeds=seeds, maxiter=int(1e6), max_calls=int(r["max_calls"]),
+                         fglob=r["fglob"], tol=1e-8)
+        lo, hi = _wilson(int(r["success"].sum()), n)
+        assert lo - 1e-9 <= g.hit.mean() <= hi + 1e-9, (r["functor"], r["dim"], g.hit.mean(), lo, hi)
+        so = np.sort(r["ncall"])
+        med = np.median(g.ncall_hit)
+        assert so[33] <= med <= so[66], (r["functor"], r["dim"], med, so[33], so[66])
+        inside95 += int(so[39] <= med <= so[60])
+        p = mannwhitneyu(g.ncall_hit, r["ncall"], alternative="two-sided").pvalue
+        assert p > 1e-3, (r["functor"], r["dim"], p, med, np.median(r["ncall"]))
+    assert inside95 >= 0.7 * len(rows), inside95
