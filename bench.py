@@ -202,12 +202,16 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    launches = [0]
+
     def resident_step():
         batch.launch()
+        launches[0] += int(_lib.lib().sda_last_launch_count())
         gather_records()
 
     def host_step():
         batch.run_from_host()
+        launches[0] += int(_lib.lib().sda_last_launch_count())
         gather_records()
 
     def totals():
@@ -223,6 +227,7 @@ def run_ours(args):
         timed(resident_step)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    launches[0] = 0
     ms_steps, evals, ls_evals, n_ls, bad = [], 0.0, 0.0, 0.0, 0.0
     kernel_ms = []
     for _ in range(args.steps):
@@ -260,7 +265,7 @@ def run_ours(args):
                 traffic = json.load(open(tpath)).get("sda_anneal_kernel")
             except Exception:
                 traffic = None
-        roofline = {"bound": "fp64", "kernel": "sda_anneal_kernel<philox>", "achieved": achieved,
+        roofline = {"bound": "fp64", "kernel": "sda_anneal_kernel<philox> (+ sda_ls_phase_kernel when phased)", "achieved": achieved,
                     "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                     "traffic": traffic,
                     "peak_source": "DFMA microbenchmark run in this process (sda_fp64_peak); "
@@ -284,7 +289,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes() * world,
                         "d2h_bytes_per_step": batch.d2h_bytes() * world,
                         "ms_per_step": float(np.mean(e2e_ms))},
-                "gpu_launches": 2 * args.steps * world,
+                "gpu_launches": launches[0] * world,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "breakdown": {"evals_per_step": evals / args.steps,
                               "chain_steps_per_s": (evals - ls_evals) / total_s,

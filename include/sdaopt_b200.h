@@ -11,7 +11,10 @@
  *    synchronize internally; the others take DEVICE pointers, never allocate and never synchronize
  *  - every function returns SDA_OK (0) or a negative SDA_E_* code; sda_error_string() decodes it;
  *    there is no CPU fallback: without a usable CUDA device the calls fail with SDA_E_CUDA
- *  - all arithmetic is IEEE double; chains are independent; one launch = one problem
+ *  - all arithmetic is IEEE double; chains are independent; one call = one problem.  Large Philox
+ *    batches with local search run as bounded rounds of { annealing launch, local-search launch }
+ *    on the caller's stream (SDA_PHASED=0 forces the single persistent launch); both paths give
+ *    bit-identical results
  *
  * RNG protocol (production mode, SDA_RNG_PHILOX): every uniform is a pure function of
  *     Philox4x32-10( ctr = { k, attempt, (purpose << 24) | j, iter }, key = seed[chain] )
@@ -206,6 +209,10 @@ size_t sda_workspace_bytes(const SdaProblem *p, const SdaConfig *c, int64_t n_ch
 int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_chains, const double *x0,
                   const uint64_t *seeds, const double *tape, int64_t tape_len, const SdaResult *out,
                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* kernels launched by the last sda_batch_run on the calling thread (1 for the persistent path,
+ * 4 per round + 1 for the phased path) */
+long long sda_last_launch_count(void);
 
 /* HOST-pointer form of the same call (what the ctypes binding of sda() uses): allocates, copies
  * in, runs on `device`, copies out, synchronizes. */

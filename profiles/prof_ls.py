@@ -18,10 +18,13 @@ ap.add_argument("--n", type=int, default=8192)
 ap.add_argument("--dim", type=int, default=50)
 ap.add_argument("--functor", default="Rastrigin")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--near", action="store_true", help="start near local minima (integers +- 0.05), like in-run searches")
 a = ap.parse_args()
 f = sb.DeviceFunctor(a.functor, dimensions=a.dim)
 lo = np.array([b[0] for b in f.bounds]); up = np.array([b[1] for b in f.bounds])
 X = lo + np.random.RandomState(1).random_sample((a.n, a.dim)) * (up - lo)
+if a.near:
+    X = np.clip(np.round(X * 0.6) + np.random.RandomState(2).normal(size=X.shape) * 0.05, lo, up)
 p, keep = functors.make_problem(f, lo, up)
 xo = np.empty_like(X); fo = np.empty(a.n); ok = np.zeros(a.n, np.int32); nf = np.zeros(a.n, np.int64)
 for rep in range(a.reps):

@@ -41,7 +41,16 @@ struct DeviceArgs {
     unsigned long long *work_counter;
     int ls_maxiter;                 // clamp(6*dim, 100, 1000)  _sda.py:291-296
     int group;                      // lanes per chain (power of two <= 32)
+    // phased execution (annealing launch / local-search launch alternate, sda_kernels.cu)
+    int phased, round, steps_per_round;
+    struct ChainRec *recs;          // [n_chains] suspended chain state
+    double *rec_x;                  // [n_chains * dim] x_cur of suspended chains
+    int *ready_q;                   // [2 * n_chains] chains to resume (double buffered by round parity)
+    int *ls_q;                      // [n_chains] chains waiting for a local search
+    long long *qctl;                // queue counters, see QCtl
 };
+
+enum QCtl : int { kReadyHead = 0, kReadyCount = 1, kLsHead = 2, kLsCount = 3, kNextCount = 4 };
 
 // the search box in shared memory: lower, upper, upper - lower and 1 / (upper - lower)
 struct Box {
@@ -56,6 +65,13 @@ struct ChainState {
     double f_hit;
     long long trace_pos;
     int state_improved, stop, hit, status, have_best;
+};
+
+// state of a chain parked between an annealing launch and a local-search launch
+struct ChainRec {
+    ChainState st;
+    long long iter, step_i;
+    int err, ls_req;
 };
 
 // the callable handed to sda(): objective + suite monitor (bench.py:292-321)

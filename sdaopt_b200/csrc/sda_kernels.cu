@@ -71,6 +71,56 @@ __device__ __forceinline__ int call_local_search(const DeviceArgs &a, ChainState
     return ok;
 }
 
+// MarkovChain.local_search after the minimiser returned (:244-250, :261-273): executed by the lanes
+// that own the chain (a group in the persistent kernel, the whole warp in the local-search launch).
+// Returns the follow-up request (the stagnation search) or kLsNone.
+__device__ __forceinline__ int apply_ls_result(const DeviceArgs &a, ChainState &st, int req, int ok,
+                                               double e, const double *wx, double *xbest,
+                                               double *xmin, double *x_cur, const Group &g)
+{
+    const int dim = a.dim;
+    int next = kLsNone;
+    if (req == kLsFromBest) {
+        if (e < st.ebest) {                                          // :244-250
+            st.not_improved_idx = 0;
+            st.ebest = e;
+            copy_vec(xbest, wx, dim, g);
+            st.e_cur = e;
+            copy_vec(x_cur, wx, dim, g);
+        } else if (st.not_improved_idx >= st.not_improved_max_idx) {  // :261-262
+            next = kLsFromMin;
+        }
+    } else {
+        if (ok) copy_vec(xmin, wx, dim, g);                          // :265
+        st.emin = e;
+        st.not_improved_idx = 0;
+        st.not_improved_max_idx = dim;
+        if (e < st.ebest) {                                          // :269-273
+            st.ebest = st.emin;
+            copy_vec(xbest, wx, dim, g);
+            st.e_cur = e;
+            copy_vec(x_cur, wx, dim, g);
+        }
+    }
+    return next;
+}
+
+// SDARunner.result :420-428 (+ the suite record, bench.py:184-188)
+__device__ __forceinline__ void write_result(const DeviceArgs &a, long long chain, const ChainState &st,
+                                             long long iter, int err, long long tape_pos)
+{
+    a.out.fun[chain] = st.ebest;
+    a.out.nit[chain] = iter;
+    a.out.ncall[chain] = st.ncall;
+    a.out.status[chain] = err;
+    if (a.out.ncall_ls) a.out.ncall_ls[chain] = st.ncall_ls;
+    if (a.out.n_ls) a.out.n_ls[chain] = st.n_ls;
+    if (a.out.hit) a.out.hit[chain] = st.hit;
+    if (a.out.ncall_hit) a.out.ncall_hit[chain] = st.ncall_hit;
+    if (a.out.f_hit) a.out.f_hit[chain] = st.f_hit;
+    if (a.out.tape_used) a.out.tape_used[chain] = tape_pos;
+}
+
 template <bool TAPE>
 __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState &st, Rng<TAPE> &rng,
                                                  double *x_cur, const Box &bx, const double *x0,
@@ -93,8 +143,17 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 // (MarkovChain.run, 2*D evaluations) and the local searches that step triggers, for every group of
 // the warp; full-mask barriers between the phases keep the groups aligned so that 32/G chains
 // share every issued instruction, whatever step, chain or function-call count each one is at.
-template <bool TAPE>
-__global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(const DeviceArgs a)
+//
+// PHASED = true is the annealing half of the phased execution (see sda_ls_phase_kernel): a group
+// that needs a local search parks its chain in global memory, queues it and pulls the next ready
+// chain; the local-search code is not part of this instantiation, which therefore holds 3 CTAs
+// per SM.
+#ifndef SDA_PHASED_MIN_BLOCKS
+#define SDA_PHASED_MIN_BLOCKS 3
+#endif
+template <bool TAPE, bool PHASED>
+__global__ void __launch_bounds__(256, PHASED ? SDA_PHASED_MIN_BLOCKS : SDA_ANNEAL_MIN_BLOCKS)
+    sda_anneal_kernel(const DeviceArgs a)
 {
     extern __shared__ double smem[];
     const int dim = a.dim;
@@ -122,14 +181,21 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
     double *sv = x_vis + dim;
     const long long slot = (long long)blockIdx.x * warps_per_block + warp;
     double *ls_slot = a.ls_work ? a.ls_work + slot * a.ls_stride : nullptr;
-    double *ls_smem = smem + 4 * dim + (size_t)warps_per_block * NG * 3 * dim +
-                      (size_t)warp * ls_smem_doubles();
+    double *ls_smem = PHASED ? nullptr : smem + 4 * dim + (size_t)warps_per_block * NG * 3 * dim +
+                                             (size_t)warp * ls_smem_doubles();
+    // a.phased && round > 0: the chains come from the ready queue and resume from their parked state
+    // (also used by the non-PHASED instantiation to finish what the bounded rounds left over)
+    const bool resume = a.phased && a.round > 0;
+    const long long n_ready = resume ? a.qctl[kReadyCount] : a.n_chains;
+    const int *ready_cur = a.phased ? a.ready_q + (size_t)(a.round & 1) * a.n_chains : nullptr;
+    unsigned long long *pull_counter =
+        a.phased ? reinterpret_cast<unsigned long long *>(a.qctl + kReadyHead) : a.work_counter;
 
     // ---- per-group state -------------------------------------------------------------------
     ChainState st;
     Rng<TAPE> rng;
     long long chain = -1, iter = 0, step_i = 0;
-    int pending = kNone, err = 0;
+    int pending = kNone, err = 0, steps_done = 0;
     bool have = false, queue_empty = false;
     double *xbest = nullptr, *xmin = nullptr;
 
@@ -137,10 +203,10 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
         // ---- phase 0: idle groups pull the next chain -------------------------------------------
         if (!have && !queue_empty) {
             unsigned long long c = 0;
-            if (g.gl == 0) c = atomicAdd(a.work_counter, 1ULL);
+            if (g.gl == 0) c = atomicAdd(pull_counter, 1ULL);
             c = __shfl_sync(g.mask, c, 0, G);
-            if ((long long)c < a.n_chains) {
-                chain = (long long)c;
+            if ((long long)c < n_ready) {
+                chain = resume ? (long long)ready_cur[c] : (long long)c;
                 have = true;
                 st.e_cur = st.ebest = st.emin = 0.0;
                 st.not_improved_idx = 0; st.not_improved_max_idx = 1000;     // :186-187
@@ -159,8 +225,16 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
                 }
                 xbest = a.out.x + chain * dim;
                 xmin = a.xmin + chain * dim;
-                iter = 0; step_i = 0; err = 0;
+                iter = 0; step_i = 0; err = 0; steps_done = 0;
                 pending = kDoInit;
+                if (resume) {
+                    // resume a chain parked by an earlier launch
+                    const ChainRec &rec = a.recs[chain];
+                    st = rec.st; iter = rec.iter; step_i = rec.step_i; err = rec.err;
+                    copy_vec(x_cur, a.rec_x + chain * dim, dim, g);
+                    group_sync(g);
+                    pending = kStep;
+                }
             } else {
                 queue_empty = true;
             }
@@ -222,9 +296,35 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
                 step_i += 1;
             }
         }
+        if constexpr (PHASED) {
+            // park the chain: for the local-search launch if it posted a request, or straight for
+            // the next annealing launch when it used up its steps of this round (bounded rounds
+            // keep the launches balanced: no group is left running one long chain alone)
+            if (do_step) steps_done += 1;
+            const bool yield = have && !finished && ls_req == kLsNone && steps_done >= a.steps_per_round;
+            if (have && (ls_req != kLsNone || yield)) {
+                if (g.gl == 0) {
+                    ChainRec &rec = a.recs[chain];
+                    rec.st = st; rec.iter = iter; rec.step_i = step_i; rec.err = err; rec.ls_req = ls_req;
+                    if (yield) {
+                        const unsigned long long pos =
+                            atomicAdd(reinterpret_cast<unsigned long long *>(a.qctl + kNextCount), 1ULL);
+                        a.ready_q[(size_t)((a.round + 1) & 1) * a.n_chains + pos] = (int)chain;
+                    } else {
+                        const unsigned long long pos =
+                            atomicAdd(reinterpret_cast<unsigned long long *>(a.qctl + kLsCount), 1ULL);
+                        a.ls_q[pos] = (int)chain;
+                    }
+                }
+                copy_vec(a.rec_x + chain * dim, x_cur, dim, g);
+                ls_req = kLsNone;
+                have = false;
+                pending = kNone;
+            }
+        }
         // two serving rounds: a search from xbest that does not improve may be followed by the
         // stagnation search from xmin (:251-273)
-        for (int round = 0; round < 2; ++round) {
+        for (int round = 0; round < 2 && !PHASED; ++round) {
             if (!__any_sync(SDA_FULL_MASK, ls_req != kLsNone)) break;
             for (int gi = 0; gi < NG; ++gi) {
                 const int src = gi * G;
@@ -249,29 +349,8 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
                     if (st.stop) {
                         ls_req = kLsNone;
                         finished = true;
-                    } else if (req == kLsFromBest) {
-                        ls_req = kLsNone;
-                        if (e < st.ebest) {                                          // :244-250
-                            st.not_improved_idx = 0;
-                            st.ebest = e;
-                            copy_vec(xbest, wx, dim, g);
-                            st.e_cur = e;
-                            copy_vec(x_cur, wx, dim, g);
-                        } else if (st.not_improved_idx >= st.not_improved_max_idx) {  // :261-262
-                            ls_req = kLsFromMin;
-                        }
                     } else {
-                        ls_req = kLsNone;
-                        if (ok) copy_vec(xmin, wx, dim, g);                          // :265
-                        st.emin = e;
-                        st.not_improved_idx = 0;
-                        st.not_improved_max_idx = dim;
-                        if (e < st.ebest) {                                          // :269-273
-                            st.ebest = st.emin;
-                            copy_vec(xbest, wx, dim, g);
-                            st.e_cur = e;
-                            copy_vec(x_cur, wx, dim, g);
-                        }
+                        ls_req = apply_ls_result(a, st, req, ok, e, wx, xbest, xmin, x_cur, g);
                     }
                     if (!finished && (double)st.ncall >= a.maxfun) step_i = 0;        // :417-418
                 }
@@ -283,22 +362,86 @@ __global__ void __launch_bounds__(256, SDA_ANNEAL_MIN_BLOCKS) sda_anneal_kernel(
         if (have && finished) {
             if constexpr (TAPE) { if (rng.t.exhausted) err |= SDA_CHAIN_TAPE_EXHAUSTED; }
             if (g.gl == 0) {
-                a.out.fun[chain] = st.ebest;
-                a.out.nit[chain] = iter;
-                a.out.ncall[chain] = st.ncall;
-                a.out.status[chain] = err;
-                if (a.out.ncall_ls) a.out.ncall_ls[chain] = st.ncall_ls;
-                if (a.out.n_ls) a.out.n_ls[chain] = st.n_ls;
-                if (a.out.hit) a.out.hit[chain] = st.hit;
-                if (a.out.ncall_hit) a.out.ncall_hit[chain] = st.ncall_hit;
-                if (a.out.f_hit) a.out.f_hit[chain] = st.f_hit;
-                if constexpr (TAPE) { if (a.out.tape_used) a.out.tape_used[chain] = rng.t.pos; }
-                else { if (a.out.tape_used) a.out.tape_used[chain] = 0; }
+                long long tape_pos = 0;
+                if constexpr (TAPE) tape_pos = rng.t.pos;
+                write_result(a, chain, st, iter, err, tape_pos);
             }
             have = false;
             pending = kNone;
         }
         __syncwarp();
+    }
+}
+
+// The local-search half of the phased execution: every warp pulls parked chains from the queue the
+// annealing launch filled, minimises (both requests of MarkovChain.local_search if the first does
+// not improve), applies the result to the parked state and queues the chain for the next
+// annealing launch -- or writes its result if the suite monitor stopped it.
+// shared memory: lower[D] upper[D] | per warp: xe[D] + L-BFGS-B matrices
+__global__ void __launch_bounds__(128, 4) sda_ls_phase_kernel(const DeviceArgs a)
+{
+    extern __shared__ double smem[];
+    const int dim = a.dim;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double *lo = smem, *up = smem + dim;
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) { lo[k] = a.lower[k]; up[k] = a.upper[k]; }
+    __syncthreads();
+    double *xe = smem + 2 * dim + (size_t)warp * (dim + ls_smem_doubles());
+    double *ls_smem = xe + dim;
+    const long long slot = (long long)blockIdx.x * wpb + warp;
+    double *ls_slot = a.ls_work + slot * a.ls_stride;
+    const long long n_ls = a.qctl[kLsCount];
+    int *ready_next = a.ready_q + (size_t)((a.round + 1) & 1) * a.n_chains;
+    const Group w32 = make_group(SDA_WARP, lane);
+    for (;;) {
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(reinterpret_cast<unsigned long long *>(a.qctl + kLsHead), 1ULL);
+        c = __shfl_sync(SDA_FULL_MASK, c, 0);
+        if ((long long)c >= n_ls) break;
+        const long long chain = a.ls_q[c];
+        const ChainRec rec = a.recs[chain];
+        ChainState st = rec.st;
+        long long step_i = rec.step_i;
+        int req = rec.ls_req;
+        bool finished = false;
+        double *xbest = a.out.x + chain * dim;
+        double *xmin = a.xmin + chain * dim;
+        double *x_cur = a.rec_x + chain * dim;
+        for (int r = 0; r < 2 && req != kLsNone; ++r) {
+            double e;
+            const int ok = call_local_search(a, st, ls_slot, ls_smem, req == kLsFromBest ? xbest : xmin,
+                                             xe, lo, up, e, lane);
+            const double *wx = ls_slot + 2LL * kLsM * dim + 6LL * dim;   // LsWork::x
+            if (st.stop) { finished = true; req = kLsNone; }
+            else req = apply_ls_result(a, st, req, ok, e, wx, xbest, xmin, x_cur, w32);
+            if (!finished && (double)st.ncall >= a.maxfun) step_i = 0;                 // :417-418
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (finished) {
+                write_result(a, chain, st, rec.iter, rec.err, 0);
+            } else {
+                ChainRec &out = a.recs[chain];
+                out.st = st; out.step_i = step_i; out.ls_req = kLsNone;
+                const unsigned long long pos =
+                    atomicAdd(reinterpret_cast<unsigned long long *>(a.qctl + kNextCount), 1ULL);
+                ready_next[pos] = (int)chain;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// queue bookkeeping between the launches of a round (one thread)
+__global__ void sda_rotate_kernel(long long *qctl, int after_ls)
+{
+    if (after_ls) {
+        qctl[kReadyCount] = qctl[kNextCount];
+        qctl[kNextCount] = 0;
+        qctl[kReadyHead] = 0;
+        qctl[kLsCount] = 0;
+    } else {
+        qctl[kLsHead] = 0;
     }
 }
 
@@ -548,12 +691,12 @@ static int pick_group_user(int dim)
 }
 
 struct LaunchPlan {
-    int warps_per_block, blocks, group;
+    int warps_per_block, blocks, group, sms;
     size_t smem;
     long long slots;
 };
 
-static int plan_launch(int dim, long long n_chains, int pure_sa, int group, LaunchPlan *lp)
+static int plan_launch(int dim, long long n_chains, int pure_sa, int group, int min_blocks, LaunchPlan *lp)
 {
     int dev = 0, sms = 0, smem_max = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -566,16 +709,17 @@ static int plan_launch(int dim, long long n_chains, int pure_sa, int group, Laun
     const int ng = 32 / group;
     const size_t ls_per_warp = pure_sa ? 0 : (size_t)sda::ls_smem_doubles() * sizeof(double);
     // aim for SDA_ANNEAL_MIN_BLOCKS resident blocks: shrink the block before giving up residency
-    const size_t budget = (size_t)smem_max / SDA_ANNEAL_MIN_BLOCKS - 1024;
+    const size_t budget = (size_t)smem_max / min_blocks - 1024;
     while (wpb > 1 && (size_t)(4 + 3 * ng * wpb) * dim * sizeof(double) + wpb * ls_per_warp > budget) wpb >>= 1;
     size_t smem = (size_t)(4 + 3 * ng * wpb) * dim * sizeof(double) + wpb * ls_per_warp;
     lp->group = group;
+    lp->sms = sms;
     if (smem > (size_t)smem_max) return SDA_E_UNSUPPORTED;
     // resident blocks per SM: bounded by shared memory and by 2048 threads
     int bps = (int)((size_t)(smem_max) / (smem + 1024));
     if (bps < 1) bps = 1;
     int max_bps = 64 / wpb; // 64 warps per SM
-    if (max_bps > SDA_ANNEAL_MIN_BLOCKS * 8 / wpb) max_bps = SDA_ANNEAL_MIN_BLOCKS * 8 / wpb; // register budget
+    if (max_bps > min_blocks * 8 / wpb) max_bps = min_blocks * 8 / wpb; // register budget
     if (bps > max_bps) bps = max_bps;
     long long want = (n_chains + (long long)wpb * ng - 1) / ((long long)wpb * ng);
     long long blocks = (long long)sms * bps;
@@ -591,6 +735,9 @@ static int plan_launch(int dim, long long n_chains, int pure_sa, int group, Laun
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // workspace layout: [counter 256B][temp table][sigmax table][xmin C*D][ls slots]
+// parked-chain buffers of the phased execution
+static size_t g_off_recs, g_off_recx, g_off_rq, g_off_lq;   // set by workspace_layout (host, per call)
+
 static size_t workspace_layout(const SdaProblem *p, const SdaConfig *c, long long n_chains,
                                long long slots, size_t *off_temp, size_t *off_sig, size_t *off_xmin,
                                size_t *off_ls, long long *ls_stride)
@@ -602,9 +749,29 @@ static size_t workspace_layout(const SdaProblem *p, const SdaConfig *c, long lon
     *off_xmin = off; off += align256((size_t)n_chains * p->dim * sizeof(double));
     *off_ls = off;
     *ls_stride = (sda::ls_workspace_doubles(p->dim) + 31) & ~31LL;
-    if (!c->pure_sa) off += align256((size_t)slots * (size_t)*ls_stride * sizeof(double));
+    if (!c->pure_sa) {
+        off += align256((size_t)slots * (size_t)*ls_stride * sizeof(double));
+        g_off_recs = off; off += align256((size_t)n_chains * sizeof(sda::ChainRec));
+        g_off_recx = off; off += align256((size_t)n_chains * p->dim * sizeof(double));
+        g_off_rq = off; off += align256((size_t)2 * n_chains * sizeof(int));
+        g_off_lq = off; off += align256((size_t)n_chains * sizeof(int));
+    }
     return off;
 }
+
+// Phased execution (annealing launches alternating with local-search launches) is the default for
+// large Philox batches with local search; SDA_PHASED=0 / 1 forces the persistent / phased path.
+// Both paths run the same chain code and give bit-identical results.
+static bool use_phased(const SdaConfig *c, long long n_chains)
+{
+    if (c->pure_sa || c->rng_mode == SDA_RNG_TAPE || c->maxiter > 5000) return false;
+    const char *env = getenv("SDA_PHASED");
+    if (env) return atoi(env) == 1;
+    return n_chains >= 4096;
+}
+
+static thread_local long long g_last_launches = 0;
+extern "C" long long sda_last_launch_count(void) { return g_last_launches; }
 
 static int max_slots(void)
 {
@@ -644,14 +811,17 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     if (c->rng_mode == SDA_RNG_TAPE && (!tape || tape_len <= 0)) return SDA_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     LaunchPlan lp;
-    rc = plan_launch(p->dim, n_chains, c->pure_sa,
+    const bool phased = use_phased(c, n_chains);
+    rc = plan_launch(p->dim, n_chains, c->pure_sa || phased,
                      (p->functor == SDA_FN_USER && c->rng_mode != SDA_RNG_TAPE) ? pick_group_user(p->dim)
-                                                                                : pick_group(p->dim, c->rng_mode), &lp);
+                                                                                : pick_group(p->dim, c->rng_mode),
+                     phased ? SDA_PHASED_MIN_BLOCKS : SDA_ANNEAL_MIN_BLOCKS, &lp);
     if (rc) return rc;
     size_t off_temp, off_sig, off_xmin, off_ls;
     long long ls_stride;
-    const size_t need = workspace_layout(p, c, n_chains, lp.slots, &off_temp, &off_sig, &off_xmin,
+    const size_t need = workspace_layout(p, c, n_chains, max_slots(), &off_temp, &off_sig, &off_xmin,
                                          &off_ls, &ls_stride);
+    const size_t off_recs = g_off_recs, off_recx = g_off_recx, off_rq = g_off_rq, off_lq = g_off_lq;
     if (need > workspace_bytes) return SDA_E_WORKSPACE;
     char *ws = (char *)workspace;
 
@@ -697,13 +867,57 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     a.group = lp.group;
 
     const int threads = lp.warps_per_block * 32;
-    if (c->rng_mode == SDA_RNG_TAPE) {
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        sda::sda_anneal_kernel<true><<<lp.blocks, threads, lp.smem, stream>>>(a);
+    if (phased) {
+        // rounds of { annealing launch ; local-search launch }: a round advances every live chain to
+        // its next local-search request, so maxiter rounds always suffice; launches that find their
+        // queue empty return at once
+        a.phased = 1;
+        {
+            const char *env = getenv("SDA_STEPS_PER_ROUND");
+            a.steps_per_round = env ? atoi(env) : 8;
+            if (a.steps_per_round < 1) a.steps_per_round = 1;
+        }
+        long long n_rounds = c->maxiter / a.steps_per_round + 48;
+        {
+            const char *env = getenv("SDA_ROUNDS");
+            if (env) n_rounds = atoll(env);
+        }
+        a.recs = (sda::ChainRec *)(ws + off_recs);
+        a.rec_x = (double *)(ws + off_recx);
+        a.ready_q = (int *)(ws + off_rq);
+        a.ls_q = (int *)(ws + off_lq);
+        a.qctl = (long long *)(ws + 64);
+        CK(cudaMemsetAsync(ws + 64, 0, 64, stream));
+        const int ls_wpb = 4;
+        const size_t ls_smem = ((size_t)2 * p->dim + (size_t)ls_wpb * (p->dim + sda::ls_smem_doubles())) * sizeof(double);
+        int ls_blocks = lp.sms * 4;
+        if ((long long)ls_blocks * ls_wpb > max_slots()) ls_blocks = max_slots() / ls_wpb;
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+        for (long long r = 0; r < n_rounds; ++r) {
+            a.round = (int)r;
+            sda::sda_anneal_kernel<false, true><<<lp.blocks, threads, lp.smem, stream>>>(a);
+            sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 0);
+            sda::sda_ls_phase_kernel<<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
+            sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 1);
+        }
+        // whatever is still parked (chains that posted a request in almost every step) is finished
+        // by the persistent kernel, resuming from the ready queue
+        LaunchPlan lp2;
+        rc = plan_launch(p->dim, n_chains, 0, lp.group, SDA_ANNEAL_MIN_BLOCKS, &lp2);
+        if (rc) return rc;
+        a.round = (int)n_rounds;
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp2.smem));
+        sda::sda_anneal_kernel<false, false><<<lp2.blocks, lp2.warps_per_block * 32, lp2.smem, stream>>>(a);
+        g_last_launches = 4 * n_rounds + 1;
+    } else if (c->rng_mode == SDA_RNG_TAPE) {
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        sda::sda_anneal_kernel<true, false><<<lp.blocks, threads, lp.smem, stream>>>(a);
     } else {
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        sda::sda_anneal_kernel<false><<<lp.blocks, threads, lp.smem, stream>>>(a);
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        sda::sda_anneal_kernel<false, false><<<lp.blocks, threads, lp.smem, stream>>>(a);
     }
+    if (!phased) g_last_launches = 1;
     CK(cudaGetLastError());
     return SDA_OK;
 }

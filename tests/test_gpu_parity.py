@@ -421,3 +421,27 @@ def test_suite_statistics_match_reference(sb):
         pk = ks_2samp(g.ncall_hit, r["ncall"]).pvalue
         assert p > 1e-3 and pk > 1e-3, (r["functor"], r["dim"], p, pk, med, np.median(r["ncall"]))
     assert inside95 >= 0.6 * len(rows), inside95
+
+
+# ---- the two execution paths of sda_batch_run ---------------------------------------------------------
+def test_phased_and_persistent_paths_are_bit_identical(sb):
+    """Large Philox batches run as bounded rounds of {annealing launch, local-search launch}; the
+    single persistent launch is the other path.  Same chain code, same draws: identical bits."""
+    from sdaopt_b200 import _lib
+    f = sb.Rastrigin(20)
+    out = {}
+    old = os.environ.get("SDA_PHASED")
+    try:
+        for mode in ("0", "1"):
+            os.environ["SDA_PHASED"] = mode
+            out[mode] = sb.sda_batch(f, f.bounds, 1500, maxiter=90)
+            n = _lib.lib().sda_last_launch_count()
+            assert (n == 1) if mode == "0" else (n > 1)
+    finally:
+        if old is None:
+            os.environ.pop("SDA_PHASED", None)
+        else:
+            os.environ["SDA_PHASED"] = old
+    for k in ("x", "fun", "nit", "ncall", "ncall_ls", "n_ls", "status"):
+        np.testing.assert_array_equal(out["0"][k], out["1"][k])
+    assert (out["1"].n_ls > 0).all() and (out["1"].status == 0).all()
