@@ -378,7 +378,10 @@ __global__ void __launch_bounds__(256, PHASED ? SDA_PHASED_MIN_BLOCKS : SDA_ANNE
 // not improve), applies the result to the parked state and queues the chain for the next
 // annealing launch -- or writes its result if the suite monitor stopped it.
 // shared memory: lower[D] upper[D] | per warp: xe[D] + L-BFGS-B matrices
-__global__ void __launch_bounds__(128, 4) sda_ls_phase_kernel(const DeviceArgs a)
+#ifndef SDA_LS_MIN_BLOCKS
+#define SDA_LS_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, SDA_LS_MIN_BLOCKS) sda_ls_phase_kernel(const DeviceArgs a)
 {
     extern __shared__ double smem[];
     const int dim = a.dim;
@@ -762,12 +765,19 @@ static size_t workspace_layout(const SdaProblem *p, const SdaConfig *c, long lon
 // Phased execution (annealing launches alternating with local-search launches) is the default for
 // large Philox batches with local search; SDA_PHASED=0 / 1 forces the persistent / phased path.
 // Both paths run the same chain code and give bit-identical results.
+#ifndef SDA_LS_MIN_BLOCKS
+#define SDA_LS_MIN_BLOCKS 4
+#endif
 static bool use_phased(const SdaConfig *c, long long n_chains)
 {
     if (c->pure_sa || c->rng_mode == SDA_RNG_TAPE || c->maxiter > 5000) return false;
     const char *env = getenv("SDA_PHASED");
     if (env) return atoi(env) == 1;
-    return n_chains >= 4096;
+    // A round waits for its slowest local search, so the local-search launch needs many requests
+    // per warp to average the heavy-tailed search lengths: measured crossover for D=50 at ~12 k
+    // chains (8 k: -11 %, 16 k: +16 %, 32 k: +43 %, 64 k: +35 %); Sutton-Chen N=38 with 8 k chains
+    // is 5x slower phased.  148 SMs x 4 CTAs x 4 warps = 2368 searches run concurrently.
+    return n_chains >= 8LL * 148 * SDA_LS_MIN_BLOCKS * 4;
 }
 
 static thread_local long long g_last_launches = 0;
@@ -890,7 +900,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         CK(cudaMemsetAsync(ws + 64, 0, 64, stream));
         const int ls_wpb = 4;
         const size_t ls_smem = ((size_t)2 * p->dim + (size_t)ls_wpb * (p->dim + sda::ls_smem_doubles())) * sizeof(double);
-        int ls_blocks = lp.sms * 4;
+        int ls_blocks = lp.sms * SDA_LS_MIN_BLOCKS;
         if ((long long)ls_blocks * ls_wpb > max_slots()) ls_blocks = max_slots() / ls_wpb;
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));

@@ -29,10 +29,13 @@ __device__ __forceinline__ double eval_sutton_chen(const XV &x, int dim, const G
             if (j == i) continue;
             const double dx = xi - x[3 * j], dy = yi - x[3 * j + 1], dz = zi - x[3 * j + 2];
             const double r2 = dx * dx + dy * dy + dz * dz;
-            const double inv2 = 1.0 / r2;
+            // r^-1 by rsqrt (1 ulp) instead of an IEEE division plus a square root: r^-6 and r^-9
+            // follow by multiplication (relative error ~1e-15, inside the 1e-11 parity bound)
+            const double inv1 = rsqrt(r2);
+            const double inv2 = inv1 * inv1;
             const double inv6 = inv2 * inv2 * inv2;
             rho += inv6;
-            rep += inv6 * inv2 * sqrt(inv2);
+            rep += inv6 * inv2 * inv1;
         }
         part += 0.5 * rep - 39.432 * sqrt(rho);
     }
