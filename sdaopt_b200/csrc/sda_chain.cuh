@@ -282,14 +282,18 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                 // counter-based stream drawing is addressing, so they are computed lazily
                 bool have_clip = false;
                 double upper_sample = 0.0, lower_sample = 0.0;
+                // accepted polar pairs of this lane's coordinates first (flattened rejection loop,
+                // scratch: sv <- X, x_vis <- Y; both rows are rewritten below by the same lane)
+                polar_fill_philox<false>(rng.p, g.gl, G, dim, sv, x_vis);
                 // two coordinates per lane and trip: the two log/sqrt/exp/div chains are
                 // independent, which doubles the ILP of the FP64 pipe
                 for (int k0 = g.gl; k0 < dim; k0 += 2 * G) {
                     const int k1 = k0 + G;
                     const bool two = k1 < dim;
-                    double xg0, yg0, s0, xg1 = 0.5, yg1 = 0.5, s1 = 0.5;
-                    polar_pair_philox(rng.p, (uint32_t)k0, xg0, yg0, s0);
-                    if (two) polar_pair_philox(rng.p, (uint32_t)k1, xg1, yg1, s1);
+                    const double xg0 = sv[k0], yg0 = x_vis[k0];
+                    const double xg1 = two ? sv[k1] : 0.5, yg1 = two ? x_vis[k1] : 0.5;
+                    const double s0 = __dadd_rn(__dmul_rn(xg0, xg0), __dmul_rn(yg0, yg0));
+                    const double s1 = __dadd_rn(__dmul_rn(xg1, xg1), __dmul_rn(yg1, yg1));
                     double v0 = visit_from_polar_fast(xg0, yg0, s0, vc);
                     double v1 = visit_from_polar_fast(xg1, yg1, s1, vc);
                     if (!have_clip && (fabs(v0) > kTailLimit || (two && fabs(v1) > kTailLimit))) {
@@ -311,11 +315,13 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
             if (j == dim) {
                 // entering the one-coordinate phase: x_vis := x_cur, and (Philox) draw the D
                 // state-independent one-coordinate jumps of this step in parallel
-                copy_vec(x_vis, x_cur, dim, g);
                 if constexpr (!TAPE) {
+                    polar_fill_philox<true>(rng.p, g.gl, G, dim, sv, x_vis);
                     for (int k = g.gl; k < dim; k += G) {
                         rng.p.j = (uint32_t)(dim + k);
-                        double v = visit_sample_philox(rng.p, (uint32_t)k, vc);
+                        const double xg = sv[k], yg = x_vis[k];
+                        const double s = __dadd_rn(__dmul_rn(xg, xg), __dmul_rn(yg, yg));
+                        double v = visit_from_polar_fast(xg, yg, s, vc);
                         if (v > kTailLimit || v < -kTailLimit) {
                             double u, u2;
                             rng.p.pair(kClip, 0, 0, u, u2);
@@ -324,6 +330,7 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                         sv[k] = v;
                     }
                 }
+                copy_vec(x_vis, x_cur, dim, g);     // after the fill: x_vis was its scratch row
                 group_sync(g);
             }
             double visit;

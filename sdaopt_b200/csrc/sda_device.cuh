@@ -246,6 +246,39 @@ __device__ __forceinline__ void polar_pair_philox(const PhiloxRng &rng, uint32_t
     } while (s <= 0.0 || s >= 1.0);
 }
 
+// Accepted polar pairs for all coordinates of one lane (k = first, first + stride, ... < dim), Philox
+// source.  The acceptance loop is flattened over the lane's coordinates: every trip makes ONE
+// attempt for the lane's current coordinate; an accepted pair is stored (xs[k] = X, ys[k] = Y) and
+// the lane moves on, a rejected one bumps the attempt counter.  A warp therefore runs
+// max-over-lanes(total attempts) trips (~1.7 per coordinate at 7 coordinates per lane) instead of
+// the sum over coordinates of max-over-lanes(attempts) (~3.1 per coordinate) of a per-coordinate
+// loop.  Same counters, same "first accepted attempt" rule -> same samples as polar_pair_philox.
+// per_coord_j: the one-coordinate phase addresses draw k with j = dim + k.
+template <bool PER_COORD_J>
+__device__ __forceinline__ void polar_fill_philox(PhiloxRng rng, int first, int stride, int dim,
+                                                  double *xs, double *ys)
+{
+    int k = first;
+    uint32_t attempt = 0;
+#pragma unroll 1
+    while (k < dim) {
+        if (PER_COORD_J) rng.j = (uint32_t)(dim + k);
+        double u1, u2;
+        rng.pair(kPolar, (uint32_t)k, attempt, u1, u2);
+        const double xg = __dsub_rn(__dmul_rn(u1, 2.0), 1.0);
+        const double yg = __dsub_rn(__dmul_rn(u2, 2.0), 1.0);
+        const double s = __dadd_rn(__dmul_rn(xg, xg), __dmul_rn(yg, yg));
+        if (s > 0.0 && s < 1.0) {
+            xs[k] = xg;
+            ys[k] = yg;
+            k += stride;
+            attempt = 0;
+        } else {
+            attempt++;
+        }
+    }
+}
+
 // one visit_fn(T) draw for coordinate k, Philox source: polar rejection loop        :94-102
 __device__ __forceinline__ double visit_sample_philox(const PhiloxRng &rng, uint32_t k,
                                                       const VisitConst &vc)
