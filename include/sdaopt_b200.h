@@ -111,6 +111,143 @@ enum {
     SDA_FN_PATHOLOGICAL = 57,
     SDA_FN_RANA = 58,
     SDA_FN_ADJIMAN = 59,
+    /* catalogue part 3: the remaining go_funcs_*.py classes (ids follow class-name order) */
+    SDA_FN_AMGM = 60,
+    SDA_FN_ALPINE02 = 61,
+    SDA_FN_BARTELS_CONN = 62,
+    SDA_FN_BIGGS_EXP02 = 63,
+    SDA_FN_BIGGS_EXP03 = 64,
+    SDA_FN_BIGGS_EXP04 = 65,
+    SDA_FN_BIGGS_EXP05 = 66,
+    SDA_FN_BOHACHEVSKY2 = 67,
+    SDA_FN_BOHACHEVSKY3 = 68,
+    SDA_FN_BOX_BETTS = 69,
+    SDA_FN_BRANIN01 = 70,
+    SDA_FN_BRANIN02 = 71,
+    SDA_FN_BUKIN02 = 72,
+    SDA_FN_BUKIN04 = 73,
+    SDA_FN_CARROM_TABLE = 74,
+    SDA_FN_CHICHINADZE = 75,
+    SDA_FN_COLA = 76,
+    SDA_FN_COLVILLE = 77,
+    SDA_FN_CORANA = 78,
+    SDA_FN_CROSS_IN_TRAY = 79,
+    SDA_FN_CROSS_LEG_TABLE = 80,
+    SDA_FN_CROWNED_CROSS = 81,
+    SDA_FN_CSENDES = 82,
+    SDA_FN_DAMAVANDI = 83,
+    SDA_FN_DE_VILLIERS_GLASSER01 = 84,
+    SDA_FN_DE_VILLIERS_GLASSER02 = 85,
+    SDA_FN_DEB03 = 86,
+    SDA_FN_DECANOMIAL = 87,
+    SDA_FN_DECEPTIVE = 88,
+    SDA_FN_DECKKERS_AARTS = 89,
+    SDA_FN_DEFLECTED_CORRUGATED_SPRING = 90,
+    SDA_FN_DOLAN = 91,
+    SDA_FN_ECKERLE4 = 92,
+    SDA_FN_EGG_HOLDER = 93,
+    SDA_FN_EL_ATTAR_VIDYASAGAR_DUTTA = 94,
+    SDA_FN_EXP2 = 95,
+    SDA_FN_FREUDENSTEIN_ROTH = 96,
+    SDA_FN_GEAR = 97,
+    SDA_FN_GIUNTA = 98,
+    SDA_FN_GULF = 99,
+    SDA_FN_HANSEN = 100,
+    SDA_FN_HARTMANN3 = 101,
+    SDA_FN_HARTMANN6 = 102,
+    SDA_FN_HELICAL_VALLEY = 103,
+    SDA_FN_HOLDER_TABLE = 104,
+    SDA_FN_HOSAKI = 105,
+    SDA_FN_INFINITY = 106,
+    SDA_FN_JENNRICH_SAMPSON = 107,
+    SDA_FN_JUDGE = 108,
+    SDA_FN_KATSUURA = 109,
+    SDA_FN_KEANE = 110,
+    SDA_FN_KOWALIK = 111,
+    SDA_FN_LANGERMANN = 112,
+    SDA_FN_LENNARD_JONES = 113,
+    SDA_FN_LEVY03 = 114,
+    SDA_FN_LEVY05 = 115,
+    SDA_FN_MEYER = 116,
+    SDA_FN_MICHALEWICZ = 117,
+    SDA_FN_MIELE_CANTRELL = 118,
+    SDA_FN_MISHRA01 = 119,
+    SDA_FN_MISHRA02 = 120,
+    SDA_FN_MISHRA03 = 121,
+    SDA_FN_MISHRA04 = 122,
+    SDA_FN_MISHRA05 = 123,
+    SDA_FN_MISHRA06 = 124,
+    SDA_FN_MISHRA07 = 125,
+    SDA_FN_MISHRA08 = 126,
+    SDA_FN_MISHRA09 = 127,
+    SDA_FN_MISHRA10 = 128,
+    SDA_FN_MISHRA11 = 129,
+    SDA_FN_MULTI_MODAL = 130,
+    SDA_FN_NEEDLE_EYE = 131,
+    SDA_FN_NEW_FUNCTION01 = 132,
+    SDA_FN_NEW_FUNCTION02 = 133,
+    SDA_FN_ODD_SQUARE = 134,
+    SDA_FN_PARSOPOULOS = 135,
+    SDA_FN_PAVIANI = 136,
+    SDA_FN_PEN_HOLDER = 137,
+    SDA_FN_PENALTY01 = 138,
+    SDA_FN_PENALTY02 = 139,
+    SDA_FN_PERM_FUNCTION01 = 140,
+    SDA_FN_PERM_FUNCTION02 = 141,
+    SDA_FN_PINTER = 142,
+    SDA_FN_POWELL = 143,
+    SDA_FN_POWER_SUM = 144,
+    SDA_FN_PRICE02 = 145,
+    SDA_FN_PRICE03 = 146,
+    SDA_FN_PRICE04 = 147,
+    SDA_FN_QUADRATIC = 148,
+    SDA_FN_RATKOWSKY01 = 149,
+    SDA_FN_RATKOWSKY02 = 150,
+    SDA_FN_RIPPLE01 = 151,
+    SDA_FN_RIPPLE25 = 152,
+    SDA_FN_ROSENBROCK_MODIFIED = 153,
+    SDA_FN_ROTATED_ELLIPSE01 = 154,
+    SDA_FN_ROTATED_ELLIPSE02 = 155,
+    SDA_FN_SARGAN = 156,
+    SDA_FN_SCHAFFER02 = 157,
+    SDA_FN_SCHAFFER03 = 158,
+    SDA_FN_SCHAFFER04 = 159,
+    SDA_FN_SCHWEFEL02 = 160,
+    SDA_FN_SCHWEFEL04 = 161,
+    SDA_FN_SCHWEFEL06 = 162,
+    SDA_FN_SCHWEFEL36 = 163,
+    SDA_FN_SHEKEL05 = 164,
+    SDA_FN_SHEKEL07 = 165,
+    SDA_FN_SHEKEL10 = 166,
+    SDA_FN_SHUBERT01 = 167,
+    SDA_FN_SHUBERT03 = 168,
+    SDA_FN_SHUBERT04 = 169,
+    SDA_FN_STRETCHED_V = 170,
+    SDA_FN_TEST_TUBE_HOLDER = 171,
+    SDA_FN_THURBER = 172,
+    SDA_FN_TRECCANI = 173,
+    SDA_FN_TREFETHEN = 174,
+    SDA_FN_TRIGONOMETRIC01 = 175,
+    SDA_FN_TRIPOD = 176,
+    SDA_FN_URSEM01 = 177,
+    SDA_FN_URSEM03 = 178,
+    SDA_FN_URSEM04 = 179,
+    SDA_FN_URSEM_WAVES = 180,
+    SDA_FN_VENTER_SOBIEZCCZANSKI_SOBIESKI = 181,
+    SDA_FN_VINCENT = 182,
+    SDA_FN_WATSON = 183,
+    SDA_FN_WAYBURN_SEADER01 = 184,
+    SDA_FN_WAYBURN_SEADER02 = 185,
+    SDA_FN_WEIERSTRASS = 186,
+    SDA_FN_WHITLEY = 187,
+    SDA_FN_WOLFE = 188,
+    SDA_FN_XIN_SHE_YANG03 = 189,
+    SDA_FN_XIN_SHE_YANG04 = 190,
+    SDA_FN_XOR = 191,
+    SDA_FN_YAO_LIU04 = 192,
+    SDA_FN_YAO_LIU09 = 193,
+    SDA_FN_ZERO_SUM = 194,
+    SDA_FN_ZIMMERMAN = 195,
     SDA_FN_COUNT,
     /* user-supplied CUDA device functor (north star; replaces an arbitrary Python `func`,
      * _sda.py:440-444).  Available only in a library built with -DSDA_USER_FUNCTOR_HEADER="<file>"

@@ -265,6 +265,41 @@ def gen_objective_points():
     print("objective cases", len(rows))
 
 
+def gen_objective_points_cat3():
+    """Catalogue part 3 (functor ids 60..): points and values from the live reference classes.  No C
+    restatement exists for these; the device functors are compared with these values directly.
+    `cond` is the change of the reference value when every coordinate moves by one ulp -- the
+    resolution below which a differently ordered evaluation cannot be expected to agree."""
+    from sdaopt_b200.functors import _CATALOGUE3
+    rows = []
+    rs = np.random.RandomState(2025)
+    for name, (n_default, nd, _box, _f) in sorted(_CATALOGUE3.items()):
+        dims = [n_default, 7, 40] if nd else [n_default]
+        if name.startswith("PermFunction"):
+            dims = [2, 7]                 # j ** k overflows the reference's int64 beyond N ~ 15
+        if name == "LennardJones":
+            dims = [6, 9, 39]
+        for D in dims:
+            k = getattr(gbf, name)(dimensions=D) if nd else getattr(gbf, name)()
+            lo = np.array([b[0] for b in k.bounds], dtype=float)
+            up = np.array([b[1] for b in k.bounds], dtype=float)
+            X = lo + rs.random_sample((16, k.N)) * (up - lo)
+            if k.global_optimum is not None and len(k.global_optimum[0]) == k.N:
+                X[0] = np.array(k.global_optimum[0], dtype=float)
+            X[1] = lo
+            X[2] = up
+            with np.errstate(all="ignore"):
+                F = np.array([float(k.fun(x)) for x in X])
+                Fu = np.array([float(k.fun(np.nextafter(x, np.inf))) for x in X])
+                Fd = np.array([float(k.fun(np.nextafter(x, -np.inf))) for x in X])
+            cond = np.fmax(np.abs(Fu - F), np.abs(Fd - F))
+            rows.append(dict(functor=name, dim=k.N, params=np.zeros(0), X=X, F=F, cond=cond,
+                             fglob=k.fglob, bounds=np.array(k.bounds, dtype=float)))
+    np.savez_compressed(os.path.join(GOLD, "objective_points_cat3.npz"),
+                        rows=np.array(rows, dtype=object))
+    print("catalogue-3 objective cases", len(rows))
+
+
 def gen_sampler():
     """VisitingDistribution unit fixtures (test_sda.py:51-79)."""
     rs = ref_import.RecordingRandomState(1234)
@@ -363,6 +398,8 @@ def gen_asrun_summary():
 if __name__ == "__main__":
     if MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "objectives":
         gen_objective_points()
+    elif MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "objectives_cat3":
+        gen_objective_points_cat3()
     elif MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "suite_stats":
         gen_suite_stats()
     elif os.environ.get("SDA_GOLDEN_ONLY"):
@@ -370,6 +407,7 @@ if __name__ == "__main__":
     elif MODE == "libm":
         gen_sampler()
         gen_objective_points()
+        gen_objective_points_cat3()
         gen_trajectories()
         gen_ls_runs()
         gen_lbfgsb()

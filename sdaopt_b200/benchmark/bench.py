@@ -29,7 +29,7 @@ DIMENSIONS = [5] + list(range(10, 110, 10))                                   # 
 N_DIM_FUNC_SELECTION = ['Ackley01', 'Exponential', 'Rastrigin', 'Rosenbrock', 'Schwefel01']  # :52-55
 # catalogue classes with a device functor, at the default dimension of their class (N = 2)
 CATALOGUE = sorted(['Ackley01', 'Exponential', 'Griewank', 'Rastrigin', 'Rosenbrock', 'Schwefel01',
-                    'Schwefel26', 'Sphere'] + list(functors._CATALOGUE2))
+                    'Schwefel26', 'Sphere'] + list(functors._CATALOGUE_ALL))
 
 
 def build_job_list(names=None):
@@ -39,7 +39,7 @@ def build_job_list(names=None):
         if name in N_DIM_FUNC_SELECTION:
             for dim in DIMENSIONS:
                 jobs.append(('{0}_{1}'.format(name, dim), name, dim))
-        jobs.append((name, name, functors.DeviceFunctor(name, dimensions=None if name in functors._CATALOGUE2 else 2).N))
+        jobs.append((name, name, functors.DeviceFunctor(name, dimensions=None if name in functors._CATALOGUE_ALL else 2).N))
     return jobs
 
 

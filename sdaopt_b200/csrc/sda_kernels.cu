@@ -579,7 +579,29 @@ static int cuda_fail(cudaError_t e, const char *what)
 static const char *kFunctorNames[SDA_FN_COUNT] = {
     "Rastrigin", "ShiftedRastrigin", "Rosenbrock", "Ackley01", "Schwefel01", "Schwefel26",
     "Exponential", "SuttonChen", "Constant", "Sphere", "Griewank",
-    "Alpine01", "Brown", "Cigar", "CosineMixture", "Deb01", "DixonPrice", "Easom", "Qing", "Quintic", "Salomon", "Schwefel20", "Schwefel21", "Schwefel22", "Step", "StyblinskiTang", "Trid", "Zacharov", "SixHumpCamel", "Beale", "HimmelBlau", "Matyas", "McCormick", "GoldsteinPrice", "Levy13", "Bohachevsky1", "Bukin06", "EggCrate", "Schaffer01", "DropWave", "ThreeHumpCamel", "Zettl", "Leon", "Cube", "Brent", "Price01", "Bird", "Ackley02", "Ackley03", "Zirilli", "Wavy", "Step2", "Plateau", "Sodp", "Trigonometric02", "XinSheYang02", "SineEnvelope", "Pathological", "Rana", "Adjiman"};
+    "Alpine01", "Brown", "Cigar", "CosineMixture", "Deb01", "DixonPrice", "Easom", "Qing", "Quintic", "Salomon", "Schwefel20", "Schwefel21", "Schwefel22", "Step", "StyblinskiTang", "Trid", "Zacharov", "SixHumpCamel", "Beale", "HimmelBlau", "Matyas", "McCormick", "GoldsteinPrice", "Levy13", "Bohachevsky1", "Bukin06", "EggCrate", "Schaffer01", "DropWave", "ThreeHumpCamel", "Zettl", "Leon", "Cube", "Brent", "Price01", "Bird", "Ackley02", "Ackley03", "Zirilli", "Wavy", "Step2", "Plateau", "Sodp", "Trigonometric02", "XinSheYang02", "SineEnvelope", "Pathological", "Rana", "Adjiman",
+    "AMGM", "Alpine02", "BartelsConn", "BiggsExp02", "BiggsExp03", "BiggsExp04", "BiggsExp05",
+    "Bohachevsky2", "Bohachevsky3", "BoxBetts", "Branin01", "Branin02", "Bukin02", "Bukin04",
+    "CarromTable", "Chichinadze", "Cola", "Colville", "Corana", "CrossInTray", "CrossLegTable",
+    "CrownedCross", "Csendes", "Damavandi", "DeVilliersGlasser01", "DeVilliersGlasser02", "Deb03",
+    "Decanomial", "Deceptive", "DeckkersAarts", "DeflectedCorrugatedSpring", "Dolan", "Eckerle4",
+    "EggHolder", "ElAttarVidyasagarDutta", "Exp2", "FreudensteinRoth", "Gear", "Giunta", "Gulf",
+    "Hansen", "Hartmann3", "Hartmann6", "HelicalValley", "HolderTable", "Hosaki", "Infinity",
+    "JennrichSampson", "Judge", "Katsuura", "Keane", "Kowalik", "Langermann", "LennardJones",
+    "Levy03", "Levy05", "Meyer", "Michalewicz", "MieleCantrell", "Mishra01", "Mishra02", "Mishra03",
+    "Mishra04", "Mishra05", "Mishra06", "Mishra07", "Mishra08", "Mishra09", "Mishra10", "Mishra11",
+    "MultiModal", "NeedleEye", "NewFunction01", "NewFunction02", "OddSquare", "Parsopoulos",
+    "Paviani", "PenHolder", "Penalty01", "Penalty02", "PermFunction01", "PermFunction02", "Pinter",
+    "Powell", "PowerSum", "Price02", "Price03", "Price04", "Quadratic", "Ratkowsky01",
+    "Ratkowsky02", "Ripple01", "Ripple25", "RosenbrockModified", "RotatedEllipse01",
+    "RotatedEllipse02", "Sargan", "Schaffer02", "Schaffer03", "Schaffer04", "Schwefel02",
+    "Schwefel04", "Schwefel06", "Schwefel36", "Shekel05", "Shekel07", "Shekel10", "Shubert01",
+    "Shubert03", "Shubert04", "StretchedV", "TestTubeHolder", "Thurber", "Treccani", "Trefethen",
+    "Trigonometric01", "Tripod", "Ursem01", "Ursem03", "Ursem04", "UrsemWaves",
+    "VenterSobiezcczanskiSobieski", "Vincent", "Watson", "WayburnSeader01", "WayburnSeader02",
+    "Weierstrass", "Whitley", "Wolfe", "XinSheYang03", "XinSheYang04", "Xor", "YaoLiu04",
+    "YaoLiu09", "ZeroSum", "Zimmerman",
+};
 
 extern "C" int sda_abi_version(void) { return SDA_ABI_VERSION; }
 

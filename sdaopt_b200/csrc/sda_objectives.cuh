@@ -9,6 +9,8 @@
 
 #include "sda_device.cuh"
 
+#include "sda_objectives_cat.cuh"
+
 #ifdef SDA_USER_FUNCTOR_HEADER
 #include SDA_USER_FUNCTOR_HEADER
 #endif
@@ -258,8 +260,8 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
     case SDA_FN_USER:
         return ::sda_user_objective(x, dim, params);
 #endif
-    default:
-        return __longlong_as_double(0x7ff8000000000000LL);
+    default:  // ids 60..: the rest of the catalogue, out of line (cold code)
+        return eval_catalogue(fid, x, dim, g);
     }
 }
 

@@ -75,6 +75,291 @@ FUNCTOR_IDS.update({
     'Adjiman': 59,
 })
 
+# catalogue part 3 (ids 60..): the remaining go_funcs_*.py classes, device code in
+# csrc/sda_objectives_cat.cuh; metadata introspected from the reference classes
+FUNCTOR_IDS.update({
+    'AMGM': 60,
+    'Alpine02': 61,
+    'BartelsConn': 62,
+    'BiggsExp02': 63,
+    'BiggsExp03': 64,
+    'BiggsExp04': 65,
+    'BiggsExp05': 66,
+    'Bohachevsky2': 67,
+    'Bohachevsky3': 68,
+    'BoxBetts': 69,
+    'Branin01': 70,
+    'Branin02': 71,
+    'Bukin02': 72,
+    'Bukin04': 73,
+    'CarromTable': 74,
+    'Chichinadze': 75,
+    'Cola': 76,
+    'Colville': 77,
+    'Corana': 78,
+    'CrossInTray': 79,
+    'CrossLegTable': 80,
+    'CrownedCross': 81,
+    'Csendes': 82,
+    'Damavandi': 83,
+    'DeVilliersGlasser01': 84,
+    'DeVilliersGlasser02': 85,
+    'Deb03': 86,
+    'Decanomial': 87,
+    'Deceptive': 88,
+    'DeckkersAarts': 89,
+    'DeflectedCorrugatedSpring': 90,
+    'Dolan': 91,
+    'Eckerle4': 92,
+    'EggHolder': 93,
+    'ElAttarVidyasagarDutta': 94,
+    'Exp2': 95,
+    'FreudensteinRoth': 96,
+    'Gear': 97,
+    'Giunta': 98,
+    'Gulf': 99,
+    'Hansen': 100,
+    'Hartmann3': 101,
+    'Hartmann6': 102,
+    'HelicalValley': 103,
+    'HolderTable': 104,
+    'Hosaki': 105,
+    'Infinity': 106,
+    'JennrichSampson': 107,
+    'Judge': 108,
+    'Katsuura': 109,
+    'Keane': 110,
+    'Kowalik': 111,
+    'Langermann': 112,
+    'LennardJones': 113,
+    'Levy03': 114,
+    'Levy05': 115,
+    'Meyer': 116,
+    'Michalewicz': 117,
+    'MieleCantrell': 118,
+    'Mishra01': 119,
+    'Mishra02': 120,
+    'Mishra03': 121,
+    'Mishra04': 122,
+    'Mishra05': 123,
+    'Mishra06': 124,
+    'Mishra07': 125,
+    'Mishra08': 126,
+    'Mishra09': 127,
+    'Mishra10': 128,
+    'Mishra11': 129,
+    'MultiModal': 130,
+    'NeedleEye': 131,
+    'NewFunction01': 132,
+    'NewFunction02': 133,
+    'OddSquare': 134,
+    'Parsopoulos': 135,
+    'Paviani': 136,
+    'PenHolder': 137,
+    'Penalty01': 138,
+    'Penalty02': 139,
+    'PermFunction01': 140,
+    'PermFunction02': 141,
+    'Pinter': 142,
+    'Powell': 143,
+    'PowerSum': 144,
+    'Price02': 145,
+    'Price03': 146,
+    'Price04': 147,
+    'Quadratic': 148,
+    'Ratkowsky01': 149,
+    'Ratkowsky02': 150,
+    'Ripple01': 151,
+    'Ripple25': 152,
+    'RosenbrockModified': 153,
+    'RotatedEllipse01': 154,
+    'RotatedEllipse02': 155,
+    'Sargan': 156,
+    'Schaffer02': 157,
+    'Schaffer03': 158,
+    'Schaffer04': 159,
+    'Schwefel02': 160,
+    'Schwefel04': 161,
+    'Schwefel06': 162,
+    'Schwefel36': 163,
+    'Shekel05': 164,
+    'Shekel07': 165,
+    'Shekel10': 166,
+    'Shubert01': 167,
+    'Shubert03': 168,
+    'Shubert04': 169,
+    'StretchedV': 170,
+    'TestTubeHolder': 171,
+    'Thurber': 172,
+    'Treccani': 173,
+    'Trefethen': 174,
+    'Trigonometric01': 175,
+    'Tripod': 176,
+    'Ursem01': 177,
+    'Ursem03': 178,
+    'Ursem04': 179,
+    'UrsemWaves': 180,
+    'VenterSobiezcczanskiSobieski': 181,
+    'Vincent': 182,
+    'Watson': 183,
+    'WayburnSeader01': 184,
+    'WayburnSeader02': 185,
+    'Weierstrass': 186,
+    'Whitley': 187,
+    'Wolfe': 188,
+    'XinSheYang03': 189,
+    'XinSheYang04': 190,
+    'Xor': 191,
+    'YaoLiu04': 192,
+    'YaoLiu09': 193,
+    'ZeroSum': 194,
+    'Zimmerman': 195,
+})
+
+# LennardJones.minima (go_funcs_L.py): best known energies for 2..20 atoms
+_LJ_MINIMA = [-1.0, -3.0, -6.0, -9.103852, -12.712062, -16.505384, -19.821489, -24.113360,
+              -28.422532, -32.765970, -37.967600, -44.326801, -47.845157, -52.322627, -56.815742,
+              -61.317995, -66.530949, -72.659782, -77.1777043]
+
+_CATALOGUE3 = {
+    'AMGM': (2, True, (0.0, 10.0), 0.0),
+    'Alpine02': (2, True, (0.0, 10.0), -6.1295),
+    'BartelsConn': (2, False, (-500.0, 500.0), 1.0),
+    'BiggsExp02': (2, False, (0.0, 20.0), 0.0),
+    'BiggsExp03': (3, False, (0.0, 20.0), 0.0),
+    'BiggsExp04': (4, False, (0.0, 20.0), 0.0),
+    'BiggsExp05': (5, False, (0.0, 20.0), 0.0),
+    'Bohachevsky2': (2, False, (-100.0, 100.0), 0.0),
+    'Bohachevsky3': (2, False, (-100.0, 100.0), 0.0),
+    'BoxBetts': (3, False, [(0.9, 1.2), (9.0, 11.2), (0.9, 1.2)], 0.0),
+    'Branin01': (2, False, [(-5.0, 10.0), (0.0, 15.0)], 0.39788735772973816),
+    'Branin02': (2, False, (-5.0, 15.0), 5.558914403893825),
+    'Bukin02': (2, False, [(-15.0, -5.0), (-3.0, 3.0)], -124.75),
+    'Bukin04': (2, False, [(-15.0, -5.0), (-3.0, 3.0)], 0.0),
+    'CarromTable': (2, False, (-10.0, 10.0), -24.15681551650653),
+    'Chichinadze': (2, False, (-30.0, 30.0), -42.94438701899098),
+    'Cola': (17, False, [(0.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0), (-4.0, 4.0)], 11.7464),
+    'Colville': (4, False, (-10.0, 10.0), 0.0),
+    'Corana': (4, False, (-5.0, 5.0), 0.0),
+    'CrossInTray': (2, False, (-10.0, 10.0), -2.062611870822739),
+    'CrossLegTable': (2, False, (-10.0, 10.0), -1.0),
+    'CrownedCross': (2, False, (-10.0, 10.0), 0.0001),
+    'Csendes': (2, True, (-1.0, 1.0), float("nan")),
+    'Damavandi': (2, False, (0.0, 14.0), float("nan")),
+    'DeVilliersGlasser01': (4, False, (1.0, 100.0), 0.0),
+    'DeVilliersGlasser02': (5, False, (1.0, 60.0), 0.0),
+    'Deb03': (2, True, (-1.0, 1.0), -1.0),
+    'Decanomial': (2, False, (-10.0, 10.0), 0.0),
+    'Deceptive': (2, True, (0.0, 1.0), -1.0),
+    'DeckkersAarts': (2, False, (-20.0, 20.0), -24776.518342168),
+    'DeflectedCorrugatedSpring': (2, True, (0.0, 10.0), -1.0),
+    'Dolan': (5, False, (-100.0, 100.0), 0.0),
+    'Eckerle4': (3, False, [(0.0, 20.0), (1.0, 20.0), (10.0, 600.0)], 0.0014635887487),
+    'EggHolder': (2, True, (-512.1, 512.0), -959.640662711),
+    'ElAttarVidyasagarDutta': (2, False, (-100.0, 100.0), 1.712780354),
+    'Exp2': (2, False, (0.0, 20.0), 0.0),
+    'FreudensteinRoth': (2, False, (-10.0, 10.0), 0.0),
+    'Gear': (4, False, (12.0, 60.0), 2.7e-12),
+    'Giunta': (2, False, (-1.0, 1.0), 0.06447042053690566),
+    'Gulf': (3, False, (0.0, 50.0), 0.0),
+    'Hansen': (2, False, (-10.0, 10.0), -176.54179),
+    'Hartmann3': (3, False, (0.0, 1.0), -3.8627821478),
+    'Hartmann6': (6, False, (0.0, 1.0), -3.32236801141551),
+    'HelicalValley': (3, False, (-10.0, 10.0), 0.0),
+    'HolderTable': (2, False, (-10.0, 10.0), -19.20850256788675),
+    'Hosaki': (2, False, [(0.0, 5.0), (0.0, 6.0)], -2.3458115),
+    'Infinity': (2, True, (-1.0, 1.0), 0.0),
+    'JennrichSampson': (2, False, (-1.0, 1.0), 124.3621824),
+    'Judge': (2, False, (-10.0, 10.0), 16.0817307),
+    'Katsuura': (2, True, (0.0, 100.0), 1.0),
+    'Keane': (2, False, (0.0, 10.0), 0.0),
+    'Kowalik': (4, False, (-5.0, 5.0), 0.0003074861),
+    'Langermann': (2, False, (0.0, 10.0), -5.1621259),
+    'LennardJones': (6, True, (-4.0, 4.0), lambda n: _LJ_MINIMA[n // 3 - 2]),
+    'Levy03': (2, False, (-10.0, 10.0), 0.0),
+    'Levy05': (2, False, (-10.0, 10.0), -176.1375779),
+    'Meyer': (3, False, [(0.0, 1.0), (100.0, 1000.0), (100.0, 500.0)], 87.945855171),
+    'Michalewicz': (2, False, (0.0, 3.141592653589793), -1.8013),
+    'MieleCantrell': (4, False, (-1.0, 1.0), 0.0),
+    'Mishra01': (2, True, (0.0, 1.000000001), 2.0),
+    'Mishra02': (2, True, (0.0, 1.000000001), 2.0),
+    'Mishra03': (2, False, (-10.0, 10.0), -0.19990562),
+    'Mishra04': (2, False, (-10.0, 10.0), -0.177715264826),
+    'Mishra05': (2, False, (-10.0, 10.0), -1.019829519930646),
+    'Mishra06': (2, False, (-10.0, 10.0), -2.28395),
+    'Mishra07': (2, True, (-10.0, 10.0), 0.0),
+    'Mishra08': (2, False, (-10.0, 10.0), 0.0),
+    'Mishra09': (3, False, (-10.0, 10.0), 0.0),
+    'Mishra10': (2, False, (-10.0, 10.0), 0.0),
+    'Mishra11': (2, True, (-10.0, 10.0), 0.0),
+    'MultiModal': (2, True, (-10.0, 10.0), 0.0),
+    'NeedleEye': (2, True, (-10.0, 10.0), 1.0),
+    'NewFunction01': (2, False, (-10.0, 10.0), -0.184648852475),
+    'NewFunction02': (2, False, (-10.0, 10.0), -0.199409030092),
+    'OddSquare': (2, False, (-15.707963267948966, 15.707963267948966), -1.00846728102),
+    'Parsopoulos': (2, False, (-5.0, 5.0), 0.0),
+    'Paviani': (10, False, (2.001, 9.999), -45.7784684040686),
+    'PenHolder': (2, False, (-11.0, 11.0), -0.9635348327265058),
+    'Penalty01': (2, True, (-50.0, 50.0), 0.0),
+    'Penalty02': (2, True, (-50.0, 50.0), 0.0),
+    'PermFunction01': (2, True, lambda n: (-float(n), n + 1.0), 0.0),
+    'PermFunction02': (2, True, lambda n: (-float(n), n + 1.0), 0.0),
+    'Pinter': (2, True, (-10.0, 10.0), 0.0),
+    'Powell': (4, False, (-4.0, 5.0), 0.0),
+    'PowerSum': (4, False, (0.0, 4.0), 0.0),
+    'Price02': (2, False, (-10.0, 10.0), 0.9),
+    'Price03': (2, False, (-5.0, 5.0), 0.0),
+    'Price04': (2, False, (-50.0, 50.0), 0.0),
+    'Quadratic': (2, True, (-10.0, 10.0), -3873.72418),
+    'Ratkowsky01': (4, False, [(0.0, 1000.0), (1.0, 20.0), (0.0, 3.0), (0.1, 6.0)], 8786.404908),
+    'Ratkowsky02': (3, False, [(10.0, 200.0), (0.5, 5.0), (0.01, 0.5)], 8.0565229338),
+    'Ripple01': (2, False, (0.0, 1.0), -2.2),
+    'Ripple25': (2, False, (0.0, 1.0), -2.0),
+    'RosenbrockModified': (2, False, (-2.0, 2.0), 34.040243106640844),
+    'RotatedEllipse01': (2, False, (-500.0, 500.0), 0.0),
+    'RotatedEllipse02': (2, False, (-500.0, 500.0), 0.0),
+    'Sargan': (2, True, (-100.0, 100.0), 0.0),
+    'Schaffer02': (2, False, (-100.0, 100.0), 0.0),
+    'Schaffer03': (2, False, (-100.0, 100.0), 0.00156685),
+    'Schaffer04': (2, False, (-100.0, 100.0), 0.292579),
+    'Schwefel02': (2, True, (-100.0, 100.0), 0.0),
+    'Schwefel04': (2, True, (0.0, 10.0), 0.0),
+    'Schwefel06': (2, False, (-100.0, 100.0), 0.0),
+    'Schwefel36': (2, False, (0.0, 500.0), -3456.0),
+    'Shekel05': (4, False, (0.0, 10.0), -10.1531996791),
+    'Shekel07': (4, False, (0.0, 10.0), -10.4029405668),
+    'Shekel10': (4, False, (0.0, 10.0), -10.536409816692023),
+    'Shubert01': (2, True, (-10.0, 10.0), -186.7309),
+    'Shubert03': (2, True, (-10.0, 10.0), -24.062499),
+    'Shubert04': (2, True, (-10.0, 10.0), -29.016015),
+    'StretchedV': (2, True, (-10.0, 10.0), 0.0),
+    'TestTubeHolder': (2, False, (-10.0, 10.0), -10.872299901558),
+    'Thurber': (7, False, [(500.0, 2000.0), (500.0, 2000.0), (100.0, 1000.0), (10.0, 150.0), (0.1, 2.0), (0.1, 1.0), (0.0, 0.2)], 5642.7082397),
+    'Treccani': (2, False, (-5.0, 5.0), 0.0),
+    'Trefethen': (2, False, (-10.0, 10.0), -3.3068686474),
+    'Trigonometric01': (2, True, (0.0, 3.141592653589793), 0.0),
+    'Tripod': (2, False, (-100.0, 100.0), 0.0),
+    'Ursem01': (2, False, [(-2.5, 3.0), (-2.0, 2.0)], -4.81681406371),
+    'Ursem03': (2, False, [(-2.0, 2.0), (-1.5, 1.5)], -3.0),
+    'Ursem04': (2, False, (-2.0, 2.0), -1.5),
+    'UrsemWaves': (2, False, [(-0.9, 1.2), (-1.2, 1.2)], -8.5536),
+    'VenterSobiezcczanskiSobieski': (2, False, (-50.0, 50.0), -400.0),
+    'Vincent': (2, True, (0.25, 10.0), lambda n: -float(n)),
+    'Watson': (6, False, (-5.0, 5.0), 0.002288),
+    'WayburnSeader01': (2, False, (-5.0, 5.0), 0.0),
+    'WayburnSeader02': (2, False, (-500.0, 500.0), 0.0),
+    'Weierstrass': (2, True, (-0.5, 0.5), 0.0),
+    'Whitley': (2, True, (-10.24, 10.24), 0.0),
+    'Wolfe': (3, False, (0.0, 2.0), 0.0),
+    'XinSheYang03': (2, True, (-20.0, 20.0), -1.0),
+    'XinSheYang04': (2, True, (-10.0, 10.0), -1.0),
+    'Xor': (9, False, (-1.0, 1.0), 0.9597588),
+    'YaoLiu04': (2, True, (-10.0, 10.0), 0.0),
+    'YaoLiu09': (2, True, (-5.12, 5.12), 0.0),
+    'ZeroSum': (2, True, (-10.0, 10.0), 0.0),
+    'Zimmerman': (2, False, (0.0, 100.0), 0.0),
+}
+
 # name: (default N, n-D capable, box or per-dimension bounds, fglob or fglob(N)) -- the class
 # attributes of go_benchmark_functions/go_funcs_*.py (`_bounds`, `fglob`, `change_dimensionality`)
 _CATALOGUE2 = {
@@ -129,6 +414,9 @@ _CATALOGUE2 = {
     'Adjiman': (2, False, [(-1.0, 2.0), (-1.0, 1.0)], -2.02180678),
 }
 
+_CATALOGUE_ALL = dict(_CATALOGUE2)
+_CATALOGUE_ALL.update(_CATALOGUE3)
+
 # default box and known optimum of the catalogue classes (go_funcs_*.py `__init__`)
 _CATALOGUE = {
     "Rastrigin": ((-5.12, 5.12), 0.0),      # go_funcs_R.py:80-86
@@ -153,12 +441,14 @@ class DeviceFunctor(object):
         self.params = np.ascontiguousarray(params, dtype=np.float64).ravel()
         self.N = dimensions
         box, fglob = _CATALOGUE.get(name, (None, float("nan")))
-        if name in _CATALOGUE2:
-            n_default, _, box, fglob = _CATALOGUE2[name]
+        if name in _CATALOGUE_ALL:
+            n_default, _, box, fglob = _CATALOGUE_ALL[name]
             if self.N is None:
                 self.N = n_default
             if callable(fglob):
                 fglob = fglob(self.N)
+            if callable(box):                              # box depends on N (PermFunction01/02)
+                box = box(self.N)
         self.fglob = fglob
         self._box = box
         self.library_path = None        # set for user functors: the build that contains them

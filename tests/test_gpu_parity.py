@@ -56,6 +56,28 @@ def test_objectives_match_reference_and_oracle(sb, oracle):
         assert _energy_close(F, Fo, r["dim"], tol).all()
 
 
+def test_catalogue3_objectives_match_reference(sb):
+    """functor ids 60.. against values of the live reference classes
+    (oracle/gen_golden.py::gen_objective_points_cat3).  Tolerance: 1e-12 relative, or 32x the
+    change the reference itself shows under a one-ulp move of x (ill-conditioned points), or the
+    cancellation floor of test_objectives_match_reference_and_oracle."""
+    rows = load_golden("objective_points_cat3.npz")["rows"]
+    assert len({r["functor"] for r in rows}) == 136
+    bad = []
+    for r in rows:
+        f = _functor(sb, r["functor"], r["params"])
+        F = f(r["X"])
+        ref, cond = r["F"], np.nan_to_num(r["cond"], nan=0.0, posinf=0.0)
+        tol = np.maximum(np.maximum(1e-12 * np.abs(ref), 32 * cond), 1e-12 * 10.0 * r["dim"])
+        same_nan = np.isnan(F) & np.isnan(ref)
+        same_inf = np.isinf(F) & np.isinf(ref) & (np.sign(F) == np.sign(ref))
+        with np.errstate(invalid="ignore"):
+            ok = same_nan | same_inf | (np.abs(F - ref) <= tol)
+        if not ok.all():
+            bad.append((r["functor"], r["dim"], F[~ok][:3], ref[~ok][:3]))
+    assert not bad, bad
+
+
 def test_sutton_chen_known_answer_and_sizes(sb, oracle):
     xg = load_golden("objective_points.npz")["rows"][-3]["X"][0]
     assert sb.SuttonChen(6)(xg) == pytest.approx(-1163.9639632, abs=5e-8)      # suttonchen.py:43-52
