@@ -4,6 +4,7 @@
 // runs whole chains (SDARunner.search, _sda.py:393-418) start to finish, including the local
 // searches, so heavy-tailed run lengths (suite early exits, L-BFGS-B) balance dynamically and no
 // host round trip happens between temperature steps.
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include <math.h>
@@ -58,17 +59,26 @@ __device__ __forceinline__ ChainState bcast_state(const ChainState &s, int src)
 
 // The chain state and the L-BFGS-B work descriptor are handed to the (noinline) minimiser as
 // copies so that the annealing loop's own state never has its address taken and stays in registers.
+template <class Clock>
+__device__ __forceinline__ int call_local_search(const DeviceArgs &a, ChainState &st, double *ls_slot,
+                                                 double *ls_smem, const double *x_start, double *xe,
+                                                 const double *lo, const double *up, double &e,
+                                                 int lane, Clock &clk)
+{
+    ChainState tmp = st;
+    LsWork w;
+    w.bind(ls_slot, ls_smem, a.dim);
+    const int ok = ofw_local_search(a, tmp, w, x_start, xe, lo, up, e, lane, clk);
+    st = tmp;
+    return ok;
+}
 __device__ __forceinline__ int call_local_search(const DeviceArgs &a, ChainState &st, double *ls_slot,
                                                  double *ls_smem, const double *x_start, double *xe,
                                                  const double *lo, const double *up, double &e,
                                                  int lane)
 {
-    ChainState tmp = st;
-    LsWork w;
-    w.bind(ls_slot, ls_smem, a.dim);
-    const int ok = ofw_local_search(a, tmp, w, x_start, xe, lo, up, e, lane);
-    st = tmp;
-    return ok;
+    NoClock clk;
+    return call_local_search(a, st, ls_slot, ls_smem, x_start, xe, lo, up, e, lane, clk);
 }
 
 // MarkovChain.local_search after the minimiser returned (:244-250, :261-273): executed by the lanes
@@ -151,10 +161,16 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 #ifndef SDA_PHASED_MIN_BLOCKS
 #define SDA_PHASED_MIN_BLOCKS 3
 #endif
-template <bool TAPE, bool PHASED>
-__global__ void __launch_bounds__(256, PHASED ? SDA_PHASED_MIN_BLOCKS : SDA_ANNEAL_MIN_BLOCKS)
+// MODE: kPersistent = annealing with in-kernel local search; kPhasedAnneal = annealing half of the
+// phased execution; kPureSa = pure_sa runs (no local-search code either: the same 80-register,
+// 3-CTA shape as the phased half, +11 % over running pure SA through the persistent instantiation).
+enum KernelMode { kPersistent = 0, kPhasedAnneal = 1, kPureSa = 2 };
+template <bool TAPE, int MODE>
+__global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOCKS : SDA_ANNEAL_MIN_BLOCKS)
     sda_anneal_kernel(const DeviceArgs a)
 {
+    constexpr bool PHASED = MODE == kPhasedAnneal;
+    constexpr bool NO_LS = MODE != kPersistent;
     extern __shared__ double smem[];
     const int dim = a.dim;
     const int lane = threadIdx.x & 31;
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(256, PHASED ? SDA_PHASED_MIN_BLOCKS : SDA_ANNE
     double *sv = x_vis + dim;
     const long long slot = (long long)blockIdx.x * warps_per_block + warp;
     double *ls_slot = a.ls_work ? a.ls_work + slot * a.ls_stride : nullptr;
-    double *ls_smem = PHASED ? nullptr : smem + 4 * dim + (size_t)warps_per_block * NG * 3 * dim +
+    double *ls_smem = NO_LS ? nullptr : smem + 4 * dim + (size_t)warps_per_block * NG * 3 * dim +
                                              (size_t)warp * ls_smem_doubles();
     // a.phased && round > 0: the chains come from the ready queue and resume from their parked state
     // (also used by the non-PHASED instantiation to finish what the bounded rounds left over)
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(256, PHASED ? SDA_PHASED_MIN_BLOCKS : SDA_ANNE
                 finished = true;
             } else if ((double)st.ncall >= a.maxfun) {
                 step_i = 0;                                 // `break`: the while loop restarts at i = 0
-            } else if (!a.pure_sa) {
+            } else if (MODE != kPureSa && !a.pure_sa) {
                 if (st.state_improved) ls_req = kLsFromBest;                                   // :241
                 else if (st.not_improved_idx >= st.not_improved_max_idx) ls_req = kLsFromMin;  // :261
                 step_i += 1;
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(256, PHASED ? SDA_PHASED_MIN_BLOCKS : SDA_ANNE
         }
         // two serving rounds: a search from xbest that does not improve may be followed by the
         // stagnation search from xmin (:251-273)
-        for (int round = 0; round < 2 && !PHASED; ++round) {
+        for (int round = 0; round < 2 && !NO_LS; ++round) {
             if (!__any_sync(SDA_FULL_MASK, ls_req != kLsNone)) break;
             for (int gi = 0; gi < NG; ++gi) {
                 const int src = gi * G;
@@ -381,9 +397,20 @@ __global__ void __launch_bounds__(256, PHASED ? SDA_PHASED_MIN_BLOCKS : SDA_ANNE
 #ifndef SDA_LS_MIN_BLOCKS
 #define SDA_LS_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, SDA_LS_MIN_BLOCKS) sda_ls_phase_kernel(const DeviceArgs a)
+// SYNC: the warps of the CTA (SDA_LS_SYNC_WARPS of them, one CTA per SM) advance their searches in
+// lock step on the phase clock of sda_lbfgsb.cuh so that an SM fetches one phase's code at a time.
+#ifndef SDA_LS_SYNC_WARPS
+#define SDA_LS_SYNC_WARPS 16
+#endif
+template <bool SYNC>
+__global__ void __launch_bounds__(SYNC ? SDA_LS_SYNC_WARPS * 32 : 128, SYNC ? 16 / SDA_LS_SYNC_WARPS : SDA_LS_MIN_BLOCKS)
+    sda_ls_phase_kernel(const DeviceArgs a)
 {
     extern __shared__ double smem[];
+    __shared__ int done_warps;
+    if (threadIdx.x == 0) done_warps = 0;
+    typename std::conditional<SYNC, PhaseClock, NoClock>::type clk;
+    if constexpr (SYNC) { clk.cur = 0; clk.nthreads = (int)blockDim.x; }
     const int dim = a.dim;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double *lo = smem, *up = smem + dim;
@@ -402,6 +429,7 @@ __global__ void __launch_bounds__(128, SDA_LS_MIN_BLOCKS) sda_ls_phase_kernel(co
         c = __shfl_sync(SDA_FULL_MASK, c, 0);
         if ((long long)c >= n_ls) break;
         const long long chain = a.ls_q[c];
+        // (SYNC) requests are popped in any phase; the search itself starts at the next kPhEval
         const ChainRec rec = a.recs[chain];
         ChainState st = rec.st;
         long long step_i = rec.step_i;
@@ -413,7 +441,7 @@ __global__ void __launch_bounds__(128, SDA_LS_MIN_BLOCKS) sda_ls_phase_kernel(co
         for (int r = 0; r < 2 && req != kLsNone; ++r) {
             double e;
             const int ok = call_local_search(a, st, ls_slot, ls_smem, req == kLsFromBest ? xbest : xmin,
-                                             xe, lo, up, e, lane);
+                                             xe, lo, up, e, lane, clk);
             const double *wx = ls_slot + 2LL * kLsM * dim + 6LL * dim;   // LsWork::x
             if (st.stop) { finished = true; req = kLsNone; }
             else req = apply_ls_result(a, st, req, ok, e, wx, xbest, xmin, x_cur, w32);
@@ -432,6 +460,17 @@ __global__ void __launch_bounds__(128, SDA_LS_MIN_BLOCKS) sda_ls_phase_kernel(co
             }
         }
         __syncwarp();
+    }
+    if constexpr (SYNC) {
+        // out of work: keep the clock ticking for the warps that still search.  Warps sign off only
+        // in kPhStep and the count is read only right after the barrier that opens kPhDir, so every
+        // warp of the CTA sees the same count and they all leave on the same tick.
+        clk.enter(kPhStep);
+        if (lane == 0) atomicAdd(&done_warps, 1);
+        for (;;) {
+            clk.tick();
+            if (clk.cur == PhaseClock::read_slot() && *(volatile int *)&done_warps == wpb) break;
+        }
     }
 }
 
@@ -536,7 +575,8 @@ __global__ void __launch_bounds__(128) sda_local_search_kernel(DeviceArgs a, con
         ChainState st;
         memset(&st, 0, sizeof(st));
         double e;
-        const int ok = ofw_local_search(a, st, w, x_in + p * dim, xe, lo, up, e, lane);
+        NoClock clk;
+        const int ok = ofw_local_search(a, st, w, x_in + p * dim, xe, lo, up, e, lane, clk);
         for (int k = lane; k < dim; k += SDA_WARP) x_out[p * dim + k] = w.x[k];
         if (lane == 0) { f_out[p] = e; success[p] = ok; nfev[p] = st.ncall; }
         __syncwarp();
@@ -693,7 +733,10 @@ static long long table_entries(const SdaConfig *c)
 // D=50 runs 4 chains per warp with 7 coordinates per lane (89 % of the lanes busy in the O(D)
 // loops instead of 78 % with one chain per warp) and warp-uniform work is shared by 32/G chains.
 // Tape replay is serial by construction and keeps one chain per warp.
-static int pick_group(int dim, int rng_mode)
+// Small batches (the suite runs 100 chains per job) cannot fill the machine at that packing, and
+// the warp-wide local search serves the 32/G chains of a warp one after the other: G is widened
+// while every chain group still gets resident lanes (148 SMs x 16 warps), up to one chain per warp.
+static int pick_group(int dim, int rng_mode, long long n_chains)
 {
     if (rng_mode == SDA_RNG_TAPE) return 32;
     const char *env = getenv("SDA_GROUP");
@@ -703,6 +746,7 @@ static int pick_group(int dim, int rng_mode)
     }
     int g = 1;
     while (g < 32 && (dim + g - 1) / g > 8) g <<= 1;
+    while (g < 32 && n_chains * (2LL * g) <= 32LL * 148 * 16) g <<= 1;
     return g;
 }
 
@@ -846,8 +890,9 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     const bool phased = use_phased(c, n_chains);
     rc = plan_launch(p->dim, n_chains, c->pure_sa || phased,
                      (p->functor == SDA_FN_USER && c->rng_mode != SDA_RNG_TAPE) ? pick_group_user(p->dim)
-                                                                                : pick_group(p->dim, c->rng_mode),
-                     phased ? SDA_PHASED_MIN_BLOCKS : SDA_ANNEAL_MIN_BLOCKS, &lp);
+                                                                                : pick_group(p->dim, c->rng_mode, n_chains),
+                     (phased || (c->pure_sa && c->rng_mode != SDA_RNG_TAPE)) ? SDA_PHASED_MIN_BLOCKS
+                                                                             : SDA_ANNEAL_MIN_BLOCKS, &lp);
     if (rc) return rc;
     size_t off_temp, off_sig, off_xmin, off_ls;
     long long ls_stride;
@@ -920,17 +965,21 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         a.ls_q = (int *)(ws + off_lq);
         a.qctl = (long long *)(ws + 64);
         CK(cudaMemsetAsync(ws + 64, 0, 64, stream));
-        const int ls_wpb = 4;
+        const char *ls_env = getenv("SDA_LS_SYNC");
+        const bool ls_sync = ls_env ? atoi(ls_env) == 1 : true;    // block-synchronous launch: default
+        const int ls_wpb = ls_sync ? SDA_LS_SYNC_WARPS : 4;
         const size_t ls_smem = ((size_t)2 * p->dim + (size_t)ls_wpb * (p->dim + sda::ls_smem_doubles())) * sizeof(double);
-        int ls_blocks = lp.sms * SDA_LS_MIN_BLOCKS;
+        int ls_blocks = ls_sync ? lp.sms * (16 / SDA_LS_SYNC_WARPS) : lp.sms * SDA_LS_MIN_BLOCKS;
         if ((long long)ls_blocks * ls_wpb > max_slots()) ls_blocks = max_slots() / ls_wpb;
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPhasedAnneal>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        if (ls_sync) CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+        else CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
         for (long long r = 0; r < n_rounds; ++r) {
             a.round = (int)r;
-            sda::sda_anneal_kernel<false, true><<<lp.blocks, threads, lp.smem, stream>>>(a);
+            sda::sda_anneal_kernel<false, sda::kPhasedAnneal><<<lp.blocks, threads, lp.smem, stream>>>(a);
             sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 0);
-            sda::sda_ls_phase_kernel<<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
+            if (ls_sync) sda::sda_ls_phase_kernel<true><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
+            else sda::sda_ls_phase_kernel<false><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
             sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 1);
         }
         // whatever is still parked (chains that posted a request in almost every step) is finished
@@ -939,15 +988,18 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         rc = plan_launch(p->dim, n_chains, 0, lp.group, SDA_ANNEAL_MIN_BLOCKS, &lp2);
         if (rc) return rc;
         a.round = (int)n_rounds;
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp2.smem));
-        sda::sda_anneal_kernel<false, false><<<lp2.blocks, lp2.warps_per_block * 32, lp2.smem, stream>>>(a);
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp2.smem));
+        sda::sda_anneal_kernel<false, sda::kPersistent><<<lp2.blocks, lp2.warps_per_block * 32, lp2.smem, stream>>>(a);
         g_last_launches = 4 * n_rounds + 1;
     } else if (c->rng_mode == SDA_RNG_TAPE) {
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        sda::sda_anneal_kernel<true, false><<<lp.blocks, threads, lp.smem, stream>>>(a);
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        sda::sda_anneal_kernel<true, sda::kPersistent><<<lp.blocks, threads, lp.smem, stream>>>(a);
+    } else if (c->pure_sa) {
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPureSa>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        sda::sda_anneal_kernel<false, sda::kPureSa><<<lp.blocks, threads, lp.smem, stream>>>(a);
     } else {
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        sda::sda_anneal_kernel<false, false><<<lp.blocks, threads, lp.smem, stream>>>(a);
+        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        sda::sda_anneal_kernel<false, sda::kPersistent><<<lp.blocks, threads, lp.smem, stream>>>(a);
     }
     if (!phased) g_last_launches = 1;
     CK(cudaGetLastError());
@@ -1036,7 +1088,7 @@ extern "C" int sda_eval(const SdaProblem *p, const double *x, int64_t n, double 
     long long blocks = (n + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     sda::sda_eval_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p->functor, p->dim, p->params, x, n, f,
-                                                                       p->functor == SDA_FN_USER ? pick_group_user(p->dim) : pick_group(p->dim, SDA_RNG_PHILOX));
+                                                                       p->functor == SDA_FN_USER ? pick_group_user(p->dim) : pick_group(p->dim, SDA_RNG_PHILOX, 1LL << 40));
     CK(cudaGetLastError());
     return SDA_OK;
 }

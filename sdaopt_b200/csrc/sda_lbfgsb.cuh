@@ -941,9 +941,49 @@ __device__ __noinline__ bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st
 
 // ---- the minimiser.  w.x holds the start point on entry and the final iterate on exit.
 // Returns SciPy's warnflag: 0 converged, 1 maxiter/maxfun, 2 abnormal, -1 stopped by the monitor.
+// Phase clock of the block-synchronous local-search launch (sda_ls_sync_kernel).  The warps of a
+// CTA minimise different chains but walk the L-BFGS-B iteration in lock step: a cyclic clock of
+// three phases -- kPhDir (Cauchy point, subspace minimisation, line-search set-up), kPhEval
+// (function + finite-difference gradient), kPhStep (dcsrch/dcstep, convergence tests, BFGS update)
+// -- advanced by CTA barriers.  A warp that has nothing to do in a phase just passes its barrier.
+// All warps of an SM then fetch the same ~10-30 KB of code at a time instead of 16 different places
+// of the ~120 KB the iteration touches (ncu: 70 % of the unsynchronised launch's stall samples in
+// this code were instruction-fetch stalls).  NoClock compiles the barriers away.
+enum LsPhase { kPhDir = 0, kPhEval = 1, kPhStep = 2 };
+#ifndef SDA_LS_CLOCK_PHASES
+#define SDA_LS_CLOCK_PHASES 2     // 2: {algebra, eval} -- kPhStep and kPhDir share a phase; 3: all apart
+#endif
+struct NoClock {
+    __device__ __forceinline__ void enter(int) {}
+};
+struct PhaseClock {
+    int cur;        // clock phase this warp is in (0 .. SDA_LS_CLOCK_PHASES-1)
+    int nthreads;   // CTA size (all warps take part in every barrier)
+    static __device__ __forceinline__ int slot(int phase)
+    {
+        return SDA_LS_CLOCK_PHASES == 3 ? phase : (phase == kPhEval ? 1 : 0);
+    }
+    // warps sign off in sign_off_slot(); the count is read only in the slot after it, i.e. behind a
+    // barrier that every sign-off of the cycle precedes, so all warps read the same count
+    static __device__ __forceinline__ int sign_off_slot() { return slot(kPhStep); }
+    static __device__ __forceinline__ int read_slot() { return (slot(kPhStep) + 1) % SDA_LS_CLOCK_PHASES; }
+    __device__ __forceinline__ void tick()
+    {
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+        cur = (cur + 1 == SDA_LS_CLOCK_PHASES) ? 0 : cur + 1;
+    }
+    __device__ __forceinline__ void enter(int phase)
+    {
+        const int want = slot(phase);
+        while (cur != want) tick();
+    }
+};
+
+template <class Clock>
 __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWork &w, double *xe,
                                       const double *l, const double *u, double &f_out, int maxiter,
-                                      int lane)
+                                      int lane, Clock &clk)
 {
     const int n = w.n;
     double *x = w.x, *g = w.g;
@@ -963,6 +1003,7 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
     int iter = 0, nenter = 0, ileave = 0, info = 0, wrk = 0;
     double theta = 1.0, fold = 0.0, sbgnrm, stp = 0.0, gd = 0.0, gdold = 0.0, dtd = 0.0, stpmx = 0.0;
 
+    clk.enter(kPhEval);
     if (ls_fun_and_grad(a, st, w, x, xe, l, u, f, g, lane)) { f_out = f; return -1; }
     nfev = 1;
     sbgnrm = ls_projgr(n, l, u, x, g, lane);
@@ -970,6 +1011,7 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
 
     for (;;) {
         // ---------------- generalized Cauchy point ----------------
+        clk.enter(kPhDir);
         __syncwarp();
         if (ls_cauchy(w, x, l, u, g, theta, col, head, sbgnrm, lane)) {
             info = 0; col = 0; head = 1; theta = 1.0; iupdat = 0; updatd = 0;
@@ -1030,6 +1072,7 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
             fold = f; ifun = 0; iback = 0;
             int first = 1;
             for (;;) {
+                if (!first) clk.enter(kPhStep);     // the set-up call of dcsrch stays in kPhDir
                 double s1 = 0.0;
                 for (int i = lane; i < n; i += SDA_WARP) s1 += g[i] * w.d[i];
                 gd = warp_sum(s1);
@@ -1066,6 +1109,7 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
                     break;
                 }
                 if (lstask == kLsFG) {
+                    clk.enter(kPhEval);
                     if (ls_fun_and_grad(a, st, w, x, xe, l, u, f, g, lane)) { f_out = f; return -1; }
                     continue;
                 }
@@ -1119,15 +1163,16 @@ __device__ inline int lbfgsb_minimize(const DeviceArgs &a, ChainState &st, LsWor
 
 // ObjectiveFunWrapper.local_search                                                 :347-351
 // Start point x_start (any memory), result in w.x; returns 1 on success, e = 1e16 otherwise.
+template <class Clock>
 __device__ __noinline__ int ofw_local_search(const DeviceArgs &a, ChainState &st, LsWork &w,
                                        const double *x_start, double *xe, const double *lo,
-                                       const double *up, double &e, int lane)
+                                       const double *up, double &e, int lane, Clock &clk)
 {
     for (int k = lane; k < a.dim; k += SDA_WARP) w.x[k] = x_start[k];
     __syncwarp();
     st.n_ls += 1;
     w.cache_valid = 0;
-    const int warnflag = lbfgsb_minimize(a, st, w, xe, lo, up, e, a.ls_maxiter, lane);
+    const int warnflag = lbfgsb_minimize(a, st, w, xe, lo, up, e, a.ls_maxiter, lane, clk);
     __syncwarp();
     if (warnflag != 0) { e = kBigValue; return 0; }
     return 1;

@@ -467,3 +467,25 @@ def test_phased_and_persistent_paths_are_bit_identical(sb):
     for k in ("x", "fun", "nit", "ncall", "ncall_ls", "n_ls", "status"):
         np.testing.assert_array_equal(out["0"][k], out["1"][k])
     assert (out["1"].n_ls > 0).all() and (out["1"].status == 0).all()
+
+
+def test_block_synchronous_local_search_launch_is_bit_identical(sb):
+    """SDA_LS_SYNC=1: the local-search launch of the phased path with its warps in lock step on the
+    phase clock (one CTA of 16 warps per SM).  Only the schedule changes, not one bit of a chain."""
+    f = sb.Rastrigin(20)
+    out = {}
+    keep = {k: os.environ.get(k) for k in ("SDA_PHASED", "SDA_LS_SYNC")}
+    try:
+        os.environ["SDA_PHASED"] = "1"
+        for mode in ("0", "1"):
+            os.environ["SDA_LS_SYNC"] = mode
+            out[mode] = sb.sda_batch(f, f.bounds, 3000, maxiter=60)
+    finally:
+        for k, v in keep.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for k in ("x", "fun", "nit", "ncall", "ncall_ls", "n_ls", "status"):
+        np.testing.assert_array_equal(out["0"][k], out["1"][k])
+    assert (out["1"].n_ls > 0).all() and (out["1"].status == 0).all()
