@@ -1,0 +1,70 @@
+"""Reference statistics of the WHOLE suite: every job the GPU suite runs
+(248 of the reference's 250), NB_RUNS = 100, run i seeded 1234 + i, through the reference's own
+SDAOptimizer (benchmark/bench.py:155-216, :256-333) imported read-only from /root/reference.
+Budget 200,000 evaluations per run instead of 1e6 to bound the CPU time (a failing run costs 13 s at
+1e6); the GPU side of the comparison uses the same budget.  Build container only.
+
+    python oracle/gen_suite_ref_full.py [n_procs]      -> tests/golden/suite_stats_ref_full.npz
+"""
+import multiprocessing
+import os
+import sys
+import time
+import warnings
+
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+BUDGET = 200000
+NB_RUNS = 100
+
+
+def run_job(job):
+    name, fname, dim = job
+    from oracle import ref_import
+    ref_import.load()
+    import sdaopt.benchmark.go_benchmark_functions as gbf
+    from sdaopt.benchmark import bench as refbench
+    klass = getattr(gbf, fname)
+    nd = name != fname                     # '<name>_<dim>' jobs pass the dimension (bench.py:108-113)
+    succ = np.zeros(NB_RUNS, np.uint8)
+    ncall = np.zeros(NB_RUNS, np.int32)
+    fval = np.zeros(NB_RUNS)
+    t0 = time.time()
+    for i in range(NB_RUNS):
+        algo = refbench.SDAOptimizer()
+        np.random.seed(1234 + i)
+        algo.prepare(name, klass, dim if nd else None)
+        algo._maxcall = BUDGET
+        try:
+            with np.errstate(all="ignore"):
+                algo.optimize()
+        except (refbench.OptimumFoundException, refbench.OptimumNotFoundException):
+            pass
+        except Exception as e:             # the reference raises on all-NaN starts; count as failure
+            algo.success = False
+            algo.fcall_success = BUDGET
+            algo.fsuccess = np.nan
+        succ[i] = bool(algo.success)
+        ncall[i] = int(algo.fcall_success) if algo.success else BUDGET
+        fval[i] = float(algo.fsuccess) if algo.fsuccess is not None else np.nan
+    return name, fname, int(algo._k.N), succ, ncall, fval, time.time() - t0
+
+
+if __name__ == "__main__":
+    from sdaopt_b200.benchmark.bench import build_job_list
+    jobs = build_job_list()
+    nproc = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    out = {}
+    t0 = time.time()
+    with multiprocessing.Pool(nproc) as pool:
+        for name, fname, n, succ, ncall, fval, dt in pool.imap_unordered(run_job, jobs, chunksize=1):
+            out[name] = dict(functor=fname, dim=n, success=succ, ncall=ncall, fvalue=fval)
+            print("%-28s N=%-4d success %5.1f%% median ncall %9.1f  (%.0f s, total %.0f s)" % (
+                name, n, 100.0 * succ.mean(), np.median(ncall), dt, time.time() - t0), flush=True)
+    rows = np.array([dict(job=k, **v) for k, v in sorted(out.items())], dtype=object)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "suite_stats_ref_full.npz"), rows=rows,
+                        budget=BUDGET, nb_runs=NB_RUNS, numpy_version=np.__version__)
+    print("wrote", len(rows), "jobs in %.0f s" % (time.time() - t0))
