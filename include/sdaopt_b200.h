@@ -351,6 +351,16 @@ int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_chains, con
  * 4 per round + 1 for the phased path) */
 long long sda_last_launch_count(void);
 
+/* Per-kernel device time of sda_batch_run calls, measured with CUDA events on the caller's stream.
+ * sda_kernel_timing(1) arms it for the calling thread (every following sda_batch_run records an
+ * event pair around each of its launches), sda_kernel_timing(0) disarms.  sda_kernel_times()
+ * waits for the recorded events, returns the accumulated milliseconds and launch counts since the
+ * last call -- index 0: annealing launches (persistent, pure-SA or phased-annealing instantiation),
+ * 1: local-search launches, 2: the final resume launch of the phased path -- and resets them.
+ * Used by bench.py for the live per-kernel roofline figures; off by default. */
+int sda_kernel_timing(int enable);
+int sda_kernel_times(double ms[3], long long launches[3]);
+
 /* HOST-pointer form of the same call (what the ctypes binding of sda() uses): allocates, copies
  * in, runs on `device`, copies out, synchronizes. */
 int sda_batch_run_host(const SdaProblem *p, const SdaConfig *c, int64_t n_chains, const double *x0,

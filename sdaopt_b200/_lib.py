@@ -18,7 +18,8 @@ CHAIN_REINIT_FAILED, CHAIN_TAPE_EXHAUSTED = 1, 2
 EXPORTS = ["sda_abi_version", "sda_has_user_functor", "sda_error_string", "sda_last_cuda_error", "sda_functor_id",
            "sda_functor_name", "sda_device_count", "sda_workspace_bytes", "sda_batch_run", "sda_last_launch_count",
            "sda_batch_run_host", "sda_eval", "sda_eval_host", "sda_visiting_host",
-           "sda_visit_fn_host", "sda_local_search_host", "sda_fp64_peak"]
+           "sda_visit_fn_host", "sda_local_search_host", "sda_fp64_peak", "sda_kernel_timing",
+           "sda_kernel_times"]
 
 
 class SdaProblem(C.Structure):
@@ -107,6 +108,10 @@ def lib(path=None):
         L.sda_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
         L.sda_has_user_functor.restype = C.c_int
         L.sda_last_launch_count.restype = C.c_longlong
+        L.sda_kernel_timing.restype = C.c_int
+        L.sda_kernel_timing.argtypes = [C.c_int]
+        L.sda_kernel_times.restype = C.c_int
+        L.sda_kernel_times.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         if L.sda_abi_version() != 1:
             raise ImportError("libsdaopt_b200.so ABI mismatch")
         _LIBS[path] = L

@@ -158,6 +158,9 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 // that needs a local search parks its chain in global memory, queues it and pulls the next ready
 // chain; the local-search code is not part of this instantiation, which therefore holds 3 CTAs
 // per SM.
+#ifndef SDA_GUIDED_WAVES
+#define SDA_GUIDED_WAVES 1
+#endif
 #ifndef SDA_PHASED_MIN_BLOCKS
 #define SDA_PHASED_MIN_BLOCKS 3
 #endif
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOC
     ChainState st;
     Rng<TAPE> rng;
     long long chain = -1, iter = 0, step_i = 0;
-    int pending = kNone, err = 0, steps_done = 0;
+    int pending = kNone, err = 0, steps_done = 0, quota = 0;
     bool have = false, queue_empty = false;
     double *xbest = nullptr, *xmin = nullptr;
 
@@ -242,6 +245,17 @@ __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOC
                 xbest = a.out.x + chain * dim;
                 xmin = a.xmin + chain * dim;
                 iter = 0; step_i = 0; err = 0; steps_done = 0;
+                if constexpr (PHASED) {
+                    // guided scheduling of the launch's tail: once less than one chain per group is
+                    // left in the queue the step quota halves (then quarters, ...), so the groups
+                    // run out of work within ~1 step of each other instead of ~steps_per_round/2
+                    // (ncu: 14 % of the group slots of a launch were idle).  A chain that yields
+                    // early simply continues in the next round; results do not depend on it.
+                    const long long left = n_ready - (long long)c;
+                    const long long groups = (long long)gridDim.x * warps_per_block * NG;
+                    quota = a.steps_per_round;
+                    for (long long lim = groups * SDA_GUIDED_WAVES; quota > 1 && left < lim; lim >>= 1) quota >>= 1;
+                }
                 pending = kDoInit;
                 if (resume) {
                     // resume a chain parked by an earlier launch
@@ -317,7 +331,7 @@ __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOC
             // the next annealing launch when it used up its steps of this round (bounded rounds
             // keep the launches balanced: no group is left running one long chain alone)
             if (do_step) steps_done += 1;
-            const bool yield = have && !finished && ls_req == kLsNone && steps_done >= a.steps_per_round;
+            const bool yield = have && !finished && ls_req == kLsNone && steps_done >= quota;
             if (have && (ls_req != kLsNone || yield)) {
                 if (g.gl == 0) {
                     ChainRec &rec = a.recs[chain];
@@ -849,6 +863,45 @@ static bool use_phased(const SdaConfig *c, long long n_chains)
 static thread_local long long g_last_launches = 0;
 extern "C" long long sda_last_launch_count(void) { return g_last_launches; }
 
+// optional per-kernel timing (include/sdaopt_b200.h: sda_kernel_timing / sda_kernel_times)
+struct TimedLaunch { cudaEvent_t a, b; int kind; };
+static thread_local bool g_timing = false;
+static thread_local std::vector<TimedLaunch> g_timed;
+struct LaunchTimer {
+    cudaStream_t s; int kind; bool on; TimedLaunch t;
+    LaunchTimer(cudaStream_t s_, int kind_) : s(s_), kind(kind_), on(g_timing)
+    {
+        if (!on) return;
+        t.kind = kind;
+        if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(t.a, s);
+    }
+    ~LaunchTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(t.b, s);
+        g_timed.push_back(t);
+    }
+};
+extern "C" int sda_kernel_timing(int enable) { g_timing = enable != 0; return SDA_OK; }
+extern "C" int sda_kernel_times(double ms[3], long long launches[3])
+{
+    if (!ms || !launches) return SDA_E_INVALID;
+    for (int i = 0; i < 3; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    int rc = SDA_OK;
+    for (TimedLaunch &t : g_timed) {
+        float dt = 0.f;
+        cudaError_t e = cudaEventSynchronize(t.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&dt, t.a, t.b);
+        if (e != cudaSuccess) rc = cuda_fail(e, "sda_kernel_times");
+        else { ms[t.kind] += dt; launches[t.kind] += 1; }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    g_timed.clear();
+    return rc;
+}
+
 static int max_slots(void)
 {
     // upper bound used for workspace sizing without touching the device: 160 SMs x 32 warps
@@ -976,10 +1029,16 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         else CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
         for (long long r = 0; r < n_rounds; ++r) {
             a.round = (int)r;
-            sda::sda_anneal_kernel<false, sda::kPhasedAnneal><<<lp.blocks, threads, lp.smem, stream>>>(a);
+            {
+                LaunchTimer tm(stream, 0);
+                sda::sda_anneal_kernel<false, sda::kPhasedAnneal><<<lp.blocks, threads, lp.smem, stream>>>(a);
+            }
             sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 0);
-            if (ls_sync) sda::sda_ls_phase_kernel<true><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
-            else sda::sda_ls_phase_kernel<false><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
+            {
+                LaunchTimer tm(stream, 1);
+                if (ls_sync) sda::sda_ls_phase_kernel<true><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
+                else sda::sda_ls_phase_kernel<false><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
+            }
             sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 1);
         }
         // whatever is still parked (chains that posted a request in almost every step) is finished
@@ -989,16 +1048,22 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         if (rc) return rc;
         a.round = (int)n_rounds;
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp2.smem));
-        sda::sda_anneal_kernel<false, sda::kPersistent><<<lp2.blocks, lp2.warps_per_block * 32, lp2.smem, stream>>>(a);
+        {
+            LaunchTimer tm(stream, 2);
+            sda::sda_anneal_kernel<false, sda::kPersistent><<<lp2.blocks, lp2.warps_per_block * 32, lp2.smem, stream>>>(a);
+        }
         g_last_launches = 4 * n_rounds + 1;
     } else if (c->rng_mode == SDA_RNG_TAPE) {
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        LaunchTimer tm(stream, 0);
         sda::sda_anneal_kernel<true, sda::kPersistent><<<lp.blocks, threads, lp.smem, stream>>>(a);
     } else if (c->pure_sa) {
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPureSa>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        LaunchTimer tm(stream, 0);
         sda::sda_anneal_kernel<false, sda::kPureSa><<<lp.blocks, threads, lp.smem, stream>>>(a);
     } else {
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        LaunchTimer tm(stream, 0);
         sda::sda_anneal_kernel<false, sda::kPersistent><<<lp.blocks, threads, lp.smem, stream>>>(a);
     }
     if (!phased) g_last_launches = 1;
