@@ -367,6 +367,10 @@ int sda_batch_run_host(const SdaProblem *p, const SdaConfig *c, int64_t n_chains
                        const uint64_t *seeds, const double *tape, int64_t tape_len,
                        const SdaResult *out, int device);
 
+/* Accuracy probe of the device elementary functions of csrc/sda_math.cuh (host pointers):
+ * kind 0: cos_2pi(x) = cos(2 pi x), 1: log_pos(x), 2: exp_any(x); out[i] = f(x[i]). */
+int sda_math_probe_host(int kind, const double *x, int64_t n, double *out, int device);
+
 /* ---- objective evaluation: replaces Benchmark.fun(x) / sutton_chen(x)
  *      (go_benchmark_functions/go_benchmark.py:15, suttonchen.py:23) for n points ----------------- */
 int sda_eval(const SdaProblem *p, const double *x, int64_t n, double *f, void *stream);

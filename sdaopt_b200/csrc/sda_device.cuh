@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "../../include/sdaopt_b200.h"
+#include "sda_math.cuh"
 
 #define SDA_WARP 32
 #define SDA_FULL_MASK 0xffffffffu
@@ -167,9 +168,9 @@ __device__ __forceinline__ double visit_from_polar(double xg, double yg, double 
 __device__ __forceinline__ double visit_from_polar_fast(double xg, double yg, double s,
                                                         const VisitConst &vc)
 {
-    const double root = sqrt(-2.0 * log(s) / s);
+    const double root = sqrt(-2.0 * log_pos(s) / s);
     const double y = root * xg;
-    return (vc.sigmax * (root * yg)) * exp(-vc.c * log(fabs(y)));
+    return (vc.sigmax * (root * yg)) * exp_any(-vc.c * log_pos(fabs(y)));
 }
 
 // C fmod(a, R) for R > 0, bit-exact, in ~8 FP64 instructions instead of libdevice's long-division

@@ -158,6 +158,9 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 // that needs a local search parks its chain in global memory, queues it and pulls the next ready
 // chain; the local-search code is not part of this instantiation, which therefore holds 3 CTAs
 // per SM.
+#ifndef SDA_GUIDED_MIN
+#define SDA_GUIDED_MIN 1
+#endif
 #ifndef SDA_GUIDED_WAVES
 #define SDA_GUIDED_WAVES 1
 #endif
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOC
                     const long long left = n_ready - (long long)c;
                     const long long groups = (long long)gridDim.x * warps_per_block * NG;
                     quota = a.steps_per_round;
-                    for (long long lim = groups * SDA_GUIDED_WAVES; quota > 1 && left < lim; lim >>= 1) quota >>= 1;
+                    for (long long lim = groups * SDA_GUIDED_WAVES; quota > SDA_GUIDED_MIN && left < lim; lim >>= 1) quota >>= 1;
                 }
                 pending = kDoInit;
                 if (resume) {
@@ -595,6 +598,15 @@ __global__ void __launch_bounds__(128) sda_local_search_kernel(DeviceArgs a, con
         if (lane == 0) { f_out[p] = e; success[p] = ok; nfev[p] = st.ncall; }
         __syncwarp();
     }
+}
+
+// accuracy probe of sda_math.cuh
+__global__ void sda_math_probe_kernel(int kind, const double *x, long long n, double *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    out[i] = kind == 0 ? cos_2pi(v) : kind == 1 ? log_pos(v) : exp_any(v);
 }
 
 // FP64 FMA throughput probe: 8 independent DFMA chains per thread
@@ -1262,6 +1274,19 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
     CK(cudaMemcpy(f_out, dfo.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (success) CK(cudaMemcpy(success, dsu.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     if (nfev) CK(cudaMemcpy(nfev, dnf.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SDA_OK;
+}
+
+extern "C" int sda_math_probe_host(int kind, const double *x, int64_t n, double *out, int device)
+{
+    if (!x || !out || n <= 0 || kind < 0 || kind > 2) return SDA_E_INVALID;
+    CK(cudaSetDevice(device));
+    DevBuf dx, dy;
+    CK(dx.upload(x, sizeof(double) * n));
+    CK(dy.alloc(sizeof(double) * n));
+    sda::sda_math_probe_kernel<<<(unsigned)((n + 255) / 256), 256>>>(kind, (const double *)dx.p, n, (double *)dy.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dy.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return SDA_OK;
 }
 

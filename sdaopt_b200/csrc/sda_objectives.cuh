@@ -56,7 +56,7 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
     case SDA_FN_RASTRIGIN: {  // go_funcs_R.py:91   10*N + sum(x^2 - 10 cos(2 pi x))
         for (int k = lane; k < dim; k += SDA_STRIDE) {
             const double v = x[k];
-            a += v * v - 10.0 * cos(kTwoPi * v);
+            a += v * v - 10.0 * cos_2pi(v);
         }
         return 10.0 * dim + group_sum(a, g);
     }
@@ -64,7 +64,7 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
         const double shift = params[0];
         for (int k = lane; k < dim; k += SDA_STRIDE) {
             const double d = x[k] - shift;
-            a += d * d - 10.0 * cos(kTwoPi * d);
+            a += d * d - 10.0 * cos_2pi(d);
         }
         return group_sum(a, g) + 10.0 * dim;
     }
@@ -80,7 +80,7 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
         for (int k = lane; k < dim; k += SDA_STRIDE) {
             const double v = x[k];
             a += v * v;
-            b += cos(kTwoPi * v);
+            b += cos_2pi(v);
         }
         a = group_sum(a, g);
         b = group_sum(b, g);

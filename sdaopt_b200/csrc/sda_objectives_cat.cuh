@@ -780,7 +780,7 @@ __device__ __noinline__ double eval_catalogue(int fid, const XV &x, int dim, con
         for (int k = lane; k < dim; k += S) a = fmax(a, fabs(x[k]));
         return group_max(a, g);
     case SDA_FN_YAO_LIU09:
-        for (int k = lane; k < dim; k += S) { const double v = x[k]; a += v * v - 10.0 * cos(kTwoPi * v) + 10; }
+        for (int k = lane; k < dim; k += S) { const double v = x[k]; a += v * v - 10.0 * cos_2pi(v) + 10; }
         return group_sum(a, g);
     case SDA_FN_ZERO_SUM: {
         for (int k = lane; k < dim; k += S) a += x[k];

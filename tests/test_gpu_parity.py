@@ -78,6 +78,54 @@ def test_catalogue3_objectives_match_reference(sb):
     assert not bad, bad
 
 
+def test_device_math_accuracy(sb):
+    """csrc/sda_math.cuh against x87 long double: log_pos and exp_any within 1.5 ulp, cos_2pi within
+    4e-16 absolute of cos(2 pi x) (exact-period reduction; what `x^2 - 10 cos(2 pi x)` needs)."""
+    from sdaopt_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(5)
+
+    def probe(kind, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        _lib.check(L.sda_math_probe_host(kind, x.ctypes.data, x.size, out.ctypes.data, 0))
+        return out
+
+    ld = np.longdouble
+    assert np.finfo(ld).nmant >= 63, "needs an extended-precision long double as the referee"
+    # cos(2 pi x): the Rastrigin boxes, the README box, wide arguments, exact special points
+    x = np.concatenate([rs.uniform(-5.12, 5.12, 200000), rs.uniform(-5.12, 10.24, 200000) - 3.14159,
+                        rs.uniform(-600, 600, 100000), rs.uniform(-1e9, 1e9, 20000),
+                        np.arange(-8, 9) * 0.125, [0.0, -0.0, 0.25, 0.75, 1e-300, 2e15, -2e15]])
+    two_pi = ld(2) * ld("3.14159265358979323846264338327950288")
+    ref = np.cos(two_pi * (x.astype(ld) - np.rint(x).astype(ld))).astype(np.float64)
+    got = probe(0, x)
+    assert np.abs(got - ref).max() <= 4e-16
+    assert probe(0, np.array([0.0, 1.0, -3.0, 0.5, 2.5]))[:].tolist() == [1.0, 1.0, 1.0, -1.0, -1.0]
+    assert np.isnan(probe(0, np.array([np.inf, np.nan]))).all()
+    # log: s in (0, 1) as the polar method feeds it, |y| over the whole normal range
+    x = np.concatenate([rs.random_sample(300000), np.exp(rs.uniform(-700, 700, 300000)),
+                        1.0 + rs.uniform(-1e-3, 1e-3, 50000), [1.0, 0.5, 2.0, 2.2250738585072014e-308, 1.7e308]])
+    ref_ld = np.log(x.astype(ld))
+    got = probe(1, x)
+    ulp = np.spacing(np.abs(ref_ld.astype(np.float64)))
+    err = np.abs(got.astype(ld) - ref_ld).astype(np.float64) / np.maximum(ulp, 5e-324)
+    assert err[x != 1.0].max() <= 1.5 and got[x == 1.0].tolist() == [0.0]
+    sp = probe(1, np.array([0.0, -1.0, np.inf, 5e-324]))
+    assert sp[0] == -np.inf and np.isnan(sp[1]) and sp[2] == np.inf and sp[3] == pytest.approx(np.log(5e-324))
+    # exp: the sampler's range -c ln|y| with c = 4.26, and the edges
+    x = np.concatenate([rs.uniform(-708, 709, 400000), rs.uniform(-2, 2, 200000), [0.0, 709.5, 710.0, -708.5, -800.0]])
+    ref_ld = np.exp(x.astype(ld))
+    got = probe(2, x)
+    fin = (x > -708.0) & (x < 709.0)
+    ulp = np.spacing(ref_ld[fin].astype(np.float64))
+    err = np.abs(got[fin].astype(ld) - ref_ld[fin]).astype(np.float64) / ulp
+    assert err.max() <= 1.5
+    assert got[x == 710.0][0] == np.inf and got[x == 709.5][0] == np.inf     # documented: +inf from 709 on
+    assert got[x == -800.0][0] == 0.0 and got[x == 0.0][0] == 1.0
+    assert np.isnan(probe(2, np.array([np.nan])))[0]
+
+
 def test_sutton_chen_known_answer_and_sizes(sb, oracle):
     xg = load_golden("objective_points.npz")["rows"][-3]["X"][0]
     assert sb.SuttonChen(6)(xg) == pytest.approx(-1163.9639632, abs=5e-8)      # suttonchen.py:43-52
