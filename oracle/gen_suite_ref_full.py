@@ -55,18 +55,39 @@ def run_job(job):
     return name, fname, int(algo._k.N), succ, ncall, fval, time.time() - t0
 
 
+def save(out, t0):
+    rows = np.array([dict(job=k, **v) for k, v in sorted(out.items())], dtype=object)
+    path = os.path.join(ROOT, "tests", "golden", "suite_stats_ref_full.npz")
+    np.savez_compressed(path + ".tmp.npz", rows=rows, budget=BUDGET, nb_runs=NB_RUNS,
+                        numpy_version=np.__version__, wall_s=time.time() - t0)
+    os.replace(path + ".tmp.npz", path)
+
+
 if __name__ == "__main__":
     from sdaopt_b200.benchmark.bench import build_job_list
     jobs = [j for j in build_job_list() if j[2] <= 10]
     nproc = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    minutes = float(sys.argv[2]) if len(sys.argv) > 2 else 1e9     # wall budget: stop handing out jobs
+    # cheapest first (median evaluations of the GPU suite run), so a bounded run covers most jobs
+    cost = {}
+    csv_path = os.path.join(ROOT, "profiles", "r1_suite_full_results.csv")
+    if os.path.exists(csv_path):
+        import csv
+        for r in list(csv.reader(open(csv_path), delimiter=",", quotechar="|"))[1:]:
+            cost[r[0]] = min(float(r[9]), BUDGET) * (1.0 if float(r[2].strip("%")) == 100.0 else 3.0)
+    jobs.sort(key=lambda j: cost.get(j[0], 1e9))
     out = {}
     t0 = time.time()
     with multiprocessing.Pool(nproc) as pool:
-        for name, fname, n, succ, ncall, fval, dt in pool.imap_unordered(run_job, jobs, chunksize=1):
+        it = pool.imap_unordered(run_job, jobs, chunksize=1)
+        for name, fname, n, succ, ncall, fval, dt in it:
             out[name] = dict(functor=fname, dim=n, success=succ, ncall=ncall, fvalue=fval)
             print("%-28s N=%-4d success %5.1f%% median ncall %9.1f  (%.0f s, total %.0f s)" % (
                 name, n, 100.0 * succ.mean(), np.median(ncall), dt, time.time() - t0), flush=True)
-    rows = np.array([dict(job=k, **v) for k, v in sorted(out.items())], dtype=object)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "suite_stats_ref_full.npz"), rows=rows,
-                        budget=BUDGET, nb_runs=NB_RUNS, numpy_version=np.__version__)
-    print("wrote", len(rows), "jobs in %.0f s" % (time.time() - t0))
+            save(out, t0)
+            if time.time() - t0 > 60.0 * minutes:
+                print("wall budget reached with %d of %d jobs" % (len(out), len(jobs)), flush=True)
+                pool.terminate()
+                break
+    save(out, t0)
+    print("wrote", len(out), "jobs in %.0f s" % (time.time() - t0))

@@ -493,6 +493,35 @@ def test_suite_statistics_match_reference(sb):
     assert inside95 >= 0.6 * len(rows), inside95
 
 
+def test_suite_statistics_match_reference_whole_catalogue(sb):
+    """The same criterion over every suite job of dimension <= 10 the reference finished on the build
+    host (tests/golden/suite_stats_ref_full.npz, oracle/gen_suite_ref_full.py: live reference,
+    NB_RUNS = 100, seeds 1234+i, budget 200,000 evaluations).  Per job, two independent samples of
+    100 runs: Fisher's exact test on the success counts, Mann-Whitney and Kolmogorov-Smirnov on
+    ncall-to-global (failures counted at the budget).  With ~200 jobs x 3 tests the family-wise
+    threshold is p > 1e-4 (Bonferroni for ~6 % overall); profiles/suite_vs_reference.py prints the
+    table."""
+    from scipy.stats import fisher_exact, ks_2samp, mannwhitneyu
+    z = load_golden("suite_stats_ref_full.npz")
+    budget, n = int(z["budget"]), int(z["nb_runs"])
+    assert len(z["rows"]) >= 80
+    seeds = np.arange(n, dtype=np.uint64) + np.uint64(1234)
+    differ = []
+    for r in z["rows"]:
+        f = sb.DeviceFunctor(r["functor"], dimensions=int(r["dim"]))
+        g = sb.sda_batch(f, f.bounds, n, seeds=seeds, maxiter=int(1e6), max_calls=budget, fglob=f.fglob,
+                         tol=1e-8)
+        ks, kr = int(g.hit.sum()), int(r["success"].sum())
+        ps = [fisher_exact([[ks, n - ks], [kr, n - kr]])[1]]
+        gn = np.where(g.hit != 0, g.ncall_hit, budget)
+        if ks or kr:
+            ps.append(mannwhitneyu(gn, r["ncall"], alternative="two-sided").pvalue)
+            ps.append(ks_2samp(gn, r["ncall"]).pvalue)
+        if np.nanmin(ps) <= 1e-4:                      # nan: both samples constant and equal
+            differ.append((r["job"], ks, kr, float(np.median(gn)), float(np.median(r["ncall"])), ps))
+    assert not differ, differ
+
+
 # ---- the two execution paths of sda_batch_run ---------------------------------------------------------
 def test_phased_and_persistent_paths_are_bit_identical(sb):
     """Large Philox batches run as bounded rounds of {annealing launch, local-search launch}; the
