@@ -83,7 +83,11 @@ __device__ __forceinline__ double exp_any(double a)
     return __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
 }
 
+#ifdef SDA_NOINLINE_LOG
+__device__ __noinline__ double log_pos(double x)
+#else
 __device__ __forceinline__ double log_pos(double x)
+#endif
 {
 #if defined(SDA_LIBDEVICE_MATH) || defined(SDA_LIBDEVICE_LOGEXP)
     return log(x);
