@@ -1039,6 +1039,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPhasedAnneal>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         if (ls_sync) CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
         else CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+        const bool debug_rounds = getenv("SDA_DEBUG_ROUNDS") != nullptr;
         for (long long r = 0; r < n_rounds; ++r) {
             a.round = (int)r;
             {
@@ -1052,6 +1053,13 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
                 else sda::sda_ls_phase_kernel<false><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
             }
             sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 1);
+            if (debug_rounds) {     // SDA_DEBUG_ROUNDS=1: queue lengths per round on stderr (synchronises!)
+                long long q[8];
+                cudaStreamSynchronize(stream);
+                cudaMemcpy(q, a.qctl, sizeof(q), cudaMemcpyDeviceToHost);
+                if (r % 8 == 0 || r + 1 == n_rounds)
+                    fprintf(stderr, "round %lld: ready for next %lld\n", r, q[sda::kReadyCount]);
+            }
         }
         // whatever is still parked (chains that posted a request in almost every step) is finished
         // by the persistent kernel, resuming from the ready queue
