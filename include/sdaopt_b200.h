@@ -368,7 +368,8 @@ int sda_batch_run_host(const SdaProblem *p, const SdaConfig *c, int64_t n_chains
                        const SdaResult *out, int device);
 
 /* Accuracy probe of the device elementary functions of csrc/sda_math.cuh (host pointers):
- * kind 0: cos_2pi(x) = cos(2 pi x), 1: log_pos(x), 2: exp_any(x); out[i] = f(x[i]). */
+ * kind 0: cos_2pi(x) = cos(2 pi x), 1: log_pos(x), 2: exp_any(x), 3: sqrt_normal(x),
+ * 4: div_normal(1.2345678901234567, x); out[i] = f(x[i]). */
 int sda_math_probe_host(int kind, const double *x, int64_t n, double *out, int device);
 
 /* ---- objective evaluation: replaces Benchmark.fun(x) / sutton_chen(x)

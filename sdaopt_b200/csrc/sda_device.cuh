@@ -168,7 +168,7 @@ __device__ __forceinline__ double visit_from_polar(double xg, double yg, double 
 __device__ __forceinline__ double visit_from_polar_fast(double xg, double yg, double s,
                                                         const VisitConst &vc)
 {
-    const double root = sqrt(-2.0 * log_pos(s) / s);
+    const double root = sqrt_normal(div_normal(-2.0 * log_pos(s), s));     // 0 < s < 1, s >= 2^-106
     const double y = root * xg;
     return (vc.sigmax * (root * yg)) * exp_any(-vc.c * log_pos(fabs(y)));
 }

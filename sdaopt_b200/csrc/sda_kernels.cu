@@ -606,7 +606,8 @@ __global__ void sda_math_probe_kernel(int kind, const double *x, long long n, do
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    out[i] = kind == 0 ? cos_2pi(v) : kind == 1 ? log_pos(v) : exp_any(v);
+    out[i] = kind == 0 ? cos_2pi(v) : kind == 1 ? log_pos(v) : kind == 2 ? exp_any(v)
+           : kind == 3 ? sqrt_normal(v) : div_normal(1.2345678901234567, v);
 }
 
 // FP64 FMA throughput probe: 8 independent DFMA chains per thread
@@ -1287,7 +1288,7 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
 
 extern "C" int sda_math_probe_host(int kind, const double *x, int64_t n, double *out, int device)
 {
-    if (!x || !out || n <= 0 || kind < 0 || kind > 2) return SDA_E_INVALID;
+    if (!x || !out || n <= 0 || kind < 0 || kind > 4) return SDA_E_INVALID;
     CK(cudaSetDevice(device));
     DevBuf dx, dy;
     CK(dx.upload(x, sizeof(double) * n));

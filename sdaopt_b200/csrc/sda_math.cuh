@@ -44,6 +44,38 @@ __constant__ double kLogC[10] = {
 
 constexpr double kMagicRint = 6755399441055744.0;   // 1.5 * 2^52
 
+// a / b and sqrt(x) for NORMAL positive b, x (and a normal quotient): MUFU seed (2^-23), two Newton
+// steps, one residual correction -- 8 branch-free instructions instead of libdevice's ~14 plus the
+// BSSY/CALL scaffolding of its special-case path.  Faithfully rounded: never more than 1 ulp off
+// (measured: the correctly rounded value in ~95 % of the square roots, ~99.9 % of the quotients).
+__device__ __forceinline__ double div_normal(double a, double b)
+{
+#ifdef SDA_LIBDEVICE_DIV
+    return __ddiv_rn(a, b);
+#endif
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    const double q = __dmul_rn(a, r);
+    return fma(fma(-q, b, a), r, q);
+}
+__device__ __forceinline__ double sqrt_normal(double x)
+{
+#ifdef SDA_LIBDEVICE_DIV
+    return sqrt(x);
+#endif
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // ~2^-22
+    const double hx = __dmul_rn(0.5, x);
+    y = fma(y, fma(-hx, __dmul_rn(y, y), 0.5), y);                 // y (1.5 - x/2 y^2)
+    y = fma(y, fma(-hx, __dmul_rn(y, y), 0.5), y);
+    const double g = __dmul_rn(x, y);                              // ~sqrt(x)
+    return fma(fma(-g, g, x), __dmul_rn(0.5, y), g);               // g + (x - g^2) y / 2
+}
+
 __device__ __forceinline__ double cos_2pi(double v)
 {
 #ifdef SDA_LIBDEVICE_MATH   // A/B switch: the libdevice calls this file replaces
@@ -102,7 +134,7 @@ __device__ __forceinline__ double log_pos(double x)
     k += i >> 20;
     const double dk = __dadd_rn(__hiloint2double(0x43300000, k ^ 0x80000000), -4503601774854144.0);  // (double)k
     const double f = __dadd_rn(m, -1.0);
-    const double s = __ddiv_rn(f, __dadd_rn(2.0, f));
+    const double s = div_normal(f, __dadd_rn(2.0, f));
     const double z = __dmul_rn(s, s);
     const double w = __dmul_rn(z, z);
     const double t1 = __dmul_rn(w, fma(w, fma(w, kLogC[5], kLogC[3]), kLogC[1]));

@@ -124,6 +124,15 @@ def test_device_math_accuracy(sb):
     assert got[x == 710.0][0] == np.inf and got[x == 709.5][0] == np.inf     # documented: +inf from 709 on
     assert got[x == -800.0][0] == 0.0 and got[x == 0.0][0] == 1.0
     assert np.isnan(probe(2, np.array([np.nan])))[0]
+    # division / square root of normal operands (sampler: -2 ln(s) / s with s >= 2^-106, its root)
+    x = np.concatenate([np.exp(rs.uniform(-73, 73, 300000)), rs.uniform(1.7, 2.42, 100000),
+                        rs.random_sample(100000) + 1e-30])
+    for kind, ref_ld in ((3, np.sqrt(x.astype(ld))), (4, ld("1.2345678901234567") / x.astype(ld))):
+        got = probe(kind, x)
+        ulp = np.spacing(ref_ld.astype(np.float64))
+        err = np.abs(got.astype(ld) - ref_ld).astype(np.float64) / ulp
+        assert err.max() <= 1.0, (kind, err.max())
+        assert (got != ref_ld.astype(np.float64)).mean() < 0.1       # faithful; mostly the rounded value
 
 
 def test_sutton_chen_known_answer_and_sizes(sb, oracle):
