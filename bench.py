@@ -134,7 +134,7 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -334,7 +334,7 @@ def run_ours(args):
                               "ls_evals_fraction": ls_evals / max(evals, 1.0),
                               "local_searches_per_step": n_ls / args.steps,
                               "chains_with_error": bad}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -351,9 +351,25 @@ def main():
     ap.add_argument("--maxiter", type=int, default=MAXITER)
     ap.add_argument("--pure-sa", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that print banners on fd 1 (NCCL's version
+    # line at communicator creation) are pointed at stderr until the result is printed
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
