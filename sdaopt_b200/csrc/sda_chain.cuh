@@ -244,7 +244,9 @@ __device__ __forceinline__ void accept_step(const DeviceArgs &a, ChainState &st,
 }
 
 // MarkovChain.run                                                                 :192-234
-template <bool TAPE>
+// VISIT_ILP: coordinates per lane and trip in the visit transform (1: smaller loop body, the
+// default everywhere; 2: two interleaved chains, kept for experiments)
+template <bool TAPE, int VISIT_ILP>
 __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, Rng<TAPE> &rng,
                                            long long chain, long long step, double temperature,
                                            double sigmax, double *x_cur, double *x_vis, double *sv,
@@ -285,11 +287,10 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                 // accepted polar pairs of this lane's coordinates first (flattened rejection loop,
                 // scratch: sv <- X, x_vis <- Y; both rows are rewritten below by the same lane)
                 polar_fill_philox<false>(rng.p, g.gl, G, dim, sv, x_vis);
-                // one coordinate per lane and trip.  (-DSDA_VISIT_ILP=2 keeps the two-coordinate
-                // variant: it paid off while libdevice's literal-laden log/exp dominated, but with
-                // the constant-table math the smaller loop body wins: 382 -> 316 ms pure SA.)
-#if !defined(SDA_VISIT_ILP) || SDA_VISIT_ILP == 1
-                for (int k = g.gl; k < dim; k += G) {
+                // one coordinate per lane and trip (VISIT_ILP == 1): with the constant-table math the
+                // smaller loop body beats two interleaved chains in the 80-register instantiations
+                // (382 -> 316 ms pure SA)
+                for (int k = g.gl; VISIT_ILP == 1 && k < dim; k += G) {
                     const double xg0 = sv[k], yg0 = x_vis[k];
                     const double s0 = __dadd_rn(__dmul_rn(xg0, xg0), __dmul_rn(yg0, yg0));
                     double v0 = visit_from_polar_fast(xg0, yg0, s0, vc);
@@ -301,10 +302,7 @@ __device__ __forceinline__ void markov_run(const DeviceArgs &a, ChainState &st, 
                     else if (v0 < -kTailLimit) v0 = __dmul_rn(-kTailLimit, lower_sample);
                     x_vis[k] = wrap_coord(__dadd_rn(v0, x_cur[k]), bx.lo[k], bx.range[k], bx.inv_range[k]);
                 }
-                for (int k0 = dim; k0 < dim; k0 += 2 * G) {
-#else
-                for (int k0 = g.gl; k0 < dim; k0 += 2 * G) {
-#endif
+                for (int k0 = g.gl; VISIT_ILP == 2 && k0 < dim; k0 += 2 * G) {
                     const int k1 = k0 + G;
                     const bool two = k1 < dim;
                     const double xg0 = sv[k0], yg0 = x_vis[k0];

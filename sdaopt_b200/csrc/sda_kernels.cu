@@ -158,6 +158,9 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 // that needs a local search parks its chain in global memory, queues it and pulls the next ready
 // chain; the local-search code is not part of this instantiation, which therefore holds 3 CTAs
 // per SM.
+#ifndef SDA_VISIT_ILP_PERSISTENT
+#define SDA_VISIT_ILP_PERSISTENT 1   // 2 measured equal (Sutton-Chen N >= 128) or slower (D=50: -7 %)
+#endif
 #ifndef SDA_GUIDED_MIN
 #define SDA_GUIDED_MIN 1
 #endif
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOC
 
         // ---- phase 3: MarkovChain.run :412 ---------------------------------------------------------
         if (do_step)
-            markov_run<TAPE>(a, st, rng, chain, step_i, temperature, sigmax, x_cur, x_vis, sv, bx,
+            markov_run<TAPE, (MODE == kPersistent ? SDA_VISIT_ILP_PERSISTENT : 1)>(a, st, rng, chain, step_i, temperature, sigmax, x_cur, x_vis, sv, bx,
                              xbest, xmin, g);
         __syncwarp();
 
@@ -954,11 +957,11 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     cudaStream_t stream = (cudaStream_t)stream_;
     LaunchPlan lp;
     const bool phased = use_phased(c, n_chains);
-    rc = plan_launch(p->dim, n_chains, c->pure_sa || phased,
-                     (p->functor == SDA_FN_USER && c->rng_mode != SDA_RNG_TAPE) ? pick_group_user(p->dim)
-                                                                                : pick_group(p->dim, c->rng_mode, n_chains),
-                     (phased || (c->pure_sa && c->rng_mode != SDA_RNG_TAPE)) ? SDA_PHASED_MIN_BLOCKS
-                                                                             : SDA_ANNEAL_MIN_BLOCKS, &lp);
+    const int group = (p->functor == SDA_FN_USER && c->rng_mode != SDA_RNG_TAPE)
+                          ? pick_group_user(p->dim) : pick_group(p->dim, c->rng_mode, n_chains);
+    rc = plan_launch(p->dim, n_chains, c->pure_sa || phased, group,
+                     (phased || (c->pure_sa && c->rng_mode != SDA_RNG_TAPE && group < 32)) ? SDA_PHASED_MIN_BLOCKS
+                                                                                          : SDA_ANNEAL_MIN_BLOCKS, &lp);
     if (rc) return rc;
     size_t off_temp, off_sig, off_xmin, off_ls;
     long long ls_stride;
@@ -1078,7 +1081,8 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         LaunchTimer tm(stream, 0);
         sda::sda_anneal_kernel<true, sda::kPersistent><<<lp.blocks, threads, lp.smem, stream>>>(a);
-    } else if (c->pure_sa) {
+    } else if (c->pure_sa && lp.group < 32) {
+        // (one chain per warp, D > 256: the 128-register instantiation is faster -- Sutton-Chen N=128: +28 %)
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPureSa>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         LaunchTimer tm(stream, 0);
         sda::sda_anneal_kernel<false, sda::kPureSa><<<lp.blocks, threads, lp.smem, stream>>>(a);
