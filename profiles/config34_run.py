@@ -16,9 +16,11 @@ for name, dim, chains, maxiter in [("Rastrigin", 10, 65536, 200), ("Ackley01", 1
                                    ("Ackley01", 100, 65536, 40), ("Schwefel26", 100, 65536, 40),
                                    ("Rastrigin", 1000, 4096, 4), ("Ackley01", 1000, 4096, 4)]:
     f = sb.DeviceFunctor(name, dimensions=dim)
-    t0 = time.perf_counter()
-    r = sb.sda_batch(f, f.bounds, chains, maxiter=maxiter)
-    dt = time.perf_counter() - t0
+    dt = 1e30
+    for rep in range(2):          # the first call of a process also loads the 8 MB module: report the warm one
+        t0 = time.perf_counter()
+        r = sb.sda_batch(f, f.bounds, chains, maxiter=maxiter)
+        dt = min(dt, time.perf_counter() - t0)
     rows.append((name, dim, chains, maxiter, dt, int(r.ncall.sum()), float(np.median(r.fun)), int((r.status != 0).sum())))
     print("config3 %-10s D=%-4d chains=%-6d maxiter=%-4d %.2f s  %.1f Mevals/s (ls %.0f%%)  median f=%.3g  errors=%d"
           % (name, dim, chains, maxiter, dt, r.ncall.sum() / dt / 1e6, 100.0 * r.ncall_ls.sum() / r.ncall.sum(),
@@ -27,8 +29,10 @@ for n_atoms, chains, maxiter in [(6, 8192, 200), (38, 8192, 12), (128, 1024, 4),
     f = sb.SuttonChen(n_atoms)
     L = 0.7 * (n_atoms / 6.0) ** (1.0 / 3.0)          # constant density box
     bounds = [(-L, L)] * (3 * n_atoms)
-    t0 = time.perf_counter()
-    r = sb.sda_batch(f, bounds, chains, maxiter=maxiter, pure_sa=(n_atoms > 38))
-    dt = time.perf_counter() - t0
+    dt = 1e30
+    for rep in range(2):
+        t0 = time.perf_counter()
+        r = sb.sda_batch(f, bounds, chains, maxiter=maxiter, pure_sa=(n_atoms > 38))
+        dt = min(dt, time.perf_counter() - t0)
     print("config4 Sutton-Chen N=%-4d D=%-5d chains=%-5d maxiter=%-4d %.2f s  %.3f Mevals/s  best f=%.6g  errors=%d"
           % (n_atoms, 3 * n_atoms, chains, maxiter, dt, r.ncall.sum() / dt / 1e6, r.fun.min(), (r.status != 0).sum()), flush=True)
