@@ -18,7 +18,17 @@ def run_all_bench(argv=None):
                         default=DEFAULT_OUTPUT_FOLDER, help='Folder where data file for optimization results are stored')
     parser.add_argument('--functions', nargs='*', default=None, help='subset of the catalogue')
     parser.add_argument('--max-calls', type=int, default=int(1e6))
+    parser.add_argument('--gpus', type=int, default=1,
+                        help='shard the jobs over this many GPUs of the node (one process per GPU)')
     args = parser.parse_args(argv)
+    if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:
+        # re-launch under torchrun: one rank per GPU, jobs dealt by expected cost (sharding.py)
+        import subprocess
+        rest = [a for a in (sys.argv[1:] if argv is None else list(argv))]
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29533'),
+               '-m', 'sdaopt_b200.benchmark.workflow'] + rest
+        return subprocess.call(cmd)
     root = logging.getLogger()
     root.setLevel(logging.INFO)
     ch = logging.StreamHandler(sys.stdout)
