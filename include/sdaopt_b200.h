@@ -248,6 +248,10 @@ enum {
     SDA_FN_YAO_LIU09 = 193,
     SDA_FN_ZERO_SUM = 194,
     SDA_FN_ZIMMERMAN = 195,
+    /* the two classes that draw random numbers inside fun() (go_funcs_S.py:1274-1280,
+     * go_funcs_X.py:47-51): counter-based noise addressed by the point, see sda_objectives_cat.cuh */
+    SDA_FN_STOCHASTIC = 196,
+    SDA_FN_XIN_SHE_YANG01 = 197,
     SDA_FN_COUNT,
     /* user-supplied CUDA device functor (north star; replaces an arbitrary Python `func`,
      * _sda.py:440-444).  Available only in a library built with -DSDA_USER_FUNCTOR_HEADER="<file>"

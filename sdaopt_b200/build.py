@@ -11,14 +11,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdaopt_b200.so")
 SOURCES = ["sda_kernels.cu"]
-HEADERS = ["sda_device.cuh", "sda_objectives.cuh", "sda_chain.cuh", "sda_lbfgsb.cuh",
+HEADERS = ["sda_device.cuh", "sda_objectives.cuh", "sda_objectives_cat.cuh", "sda_math.cuh",
+           "sda_chain.cuh", "sda_lbfgsb.cuh",
            os.path.join("..", "..", "include", "sdaopt_b200.h")]
 # --fmad=false: no implicit FMA contraction, so objective values round like the reference's numpy
 # expressions and the oracle's -ffp-contract=off C (e.g. Bukin06 at its optimum (-10, 1):
 # x1 - 0.01*x0^2 is exactly 0 in the reference, 4.6e-7 after sqrt with a contracted fma).  libdevice
 # and the explicit fma() calls of the kernels are unaffected; measured cost 7 % on the pure-SA loop.
 # -split-compile=8: the back end optimises the kernels in 8 parallel partitions (build 80 s instead
-# of 260 s for the 196-functor library; a fixed count keeps the build reproducible across hosts).
+# of 260 s for the 198-functor library; a fixed count keeps the build reproducible across hosts).
 # Measured on B200 against the unsplit build: pure SA +9 %, block-synchronous local search +2 %.
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--fmad=false", "-split-compile=8", "-Xcompiler", "-fPIC", "-shared",

@@ -670,7 +670,7 @@ static const char *kFunctorNames[SDA_FN_COUNT] = {
     "Trigonometric01", "Tripod", "Ursem01", "Ursem03", "Ursem04", "UrsemWaves",
     "VenterSobiezcczanskiSobieski", "Vincent", "Watson", "WayburnSeader01", "WayburnSeader02",
     "Weierstrass", "Whitley", "Wolfe", "XinSheYang03", "XinSheYang04", "Xor", "YaoLiu04",
-    "YaoLiu09", "ZeroSum", "Zimmerman",
+    "YaoLiu09", "ZeroSum", "Zimmerman", "Stochastic", "XinSheYang01",
 };
 
 extern "C" int sda_abi_version(void) { return SDA_ABI_VERSION; }

@@ -24,6 +24,40 @@ __device__ __forceinline__ double quart(double v) { const double t = v * v; retu
 __device__ __forceinline__ double np_sign(double v) { return (double)((v > 0.0) - (v < 0.0)); }
 __device__ __forceinline__ double nan_value() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// ---- objectives that draw random numbers inside fun() --------------------------------------------
+// Stochastic (go_funcs_S.py:1274-1280) and XinSheYang01 (go_funcs_X.py:47-51) multiply every term by
+// eps_i ~ U[0,1) drawn from NumPy's GLOBAL generator at every call, so their value at a point is not
+// a function of the point and no call-by-call parity exists.  Here eps is counter-based noise
+// addressed by the point: Philox4x32-10 with counter (hash64(x), i, tag) -> the 53-bit uniform of
+// numpy's random_sample().  Every distinct point sees independent U[0,1) factors (what the chain,
+// the finite-difference gradient and the first-hit monitor observe in the reference), a repeated
+// request at a bit-identical point repeats its value (SciPy's ScalarFunction cache does the same),
+// and the evaluation needs no per-chain state.  Restated on the CPU in oracle/rng_objectives.py.
+__device__ __forceinline__ uint64_t mix64(uint64_t z)     // splitmix64 finaliser
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <class XV>
+__device__ __forceinline__ uint64_t point_hash(const XV &x, int dim, const Group &g)
+{
+    uint64_t h = 0;
+    for (int k = g.gl; k < dim; k += g.G)
+        h += mix64((uint64_t)__double_as_longlong(x[k]) + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ull);
+    for (int o = g.G >> 1; o > 0; o >>= 1) h += __shfl_xor_sync(g.mask, h, o);
+    return h;
+}
+__device__ __forceinline__ double point_noise(uint64_t h, int k, uint32_t tag)
+{
+    Philox ph;
+    ph.k0 = 0x53444131u;   // "SDA1"
+    ph.k1 = tag;
+    uint32_t o[4];
+    ph.block((uint32_t)h, (uint32_t)(h >> 32), (uint32_t)k, 0u, o);
+    return u53(o[0], o[1]);
+}
+
 // ---- data tables of the fixed-size classes ------------------------------------------------------
 __device__ const double kColaD[45] = {   // lower triangle of Cola.d, row i = 1..9, columns j < i
     1.27,
@@ -799,6 +833,16 @@ __device__ __noinline__ double eval_catalogue(int fid, const XV &x, int dim, con
         v = fmax(v, 100.0 * (1.0 - p) * np_sign(p));
         v = fmax(v, 100.0 * (1.0 - q) * np_sign(q));
         return v;
+    }
+    case SDA_FN_STOCHASTIC: {  // sum(rnd * abs(x - 1/i)), i = 1..N
+        const uint64_t h = point_hash(x, dim, g);
+        for (int k = lane; k < dim; k += S) a += point_noise(h, k, 0x53544F43u) * fabs(x[k] - 1.0 / (double)(k + 1));
+        return group_sum(a, g);
+    }
+    case SDA_FN_XIN_SHE_YANG01: {  // sum(rnd * abs(x) ** i), i = 1..N
+        const uint64_t h = point_hash(x, dim, g);
+        for (int k = lane; k < dim; k += S) a += point_noise(h, k, 0x58535931u) * pow(fabs(x[k]), (double)(k + 1));
+        return group_sum(a, g);
     }
     default:
         return nan_value();

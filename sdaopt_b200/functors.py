@@ -214,6 +214,8 @@ FUNCTOR_IDS.update({
     'YaoLiu09': 193,
     'ZeroSum': 194,
     'Zimmerman': 195,
+    'Stochastic': 196,
+    'XinSheYang01': 197,
 })
 
 # LennardJones.minima (go_funcs_L.py): best known energies for 2..20 atoms
@@ -358,6 +360,10 @@ _CATALOGUE3 = {
     'YaoLiu09': (2, True, (-5.12, 5.12), 0.0),
     'ZeroSum': (2, True, (-10.0, 10.0), 0.0),
     'Zimmerman': (2, False, (0.0, 100.0), 0.0),
+    # fun() draws U[0,1) factors at every call (go_funcs_S.py:1274-1280, go_funcs_X.py:47-51);
+    # on the device the factors are Philox noise addressed by the point (sda_objectives_cat.cuh)
+    'Stochastic': (2, True, (-5.0, 5.0), 0.0),
+    'XinSheYang01': (2, True, (-5.0, 5.0), 0.0),
 }
 
 # name: (default N, n-D capable, box or per-dimension bounds, fglob or fglob(N)) -- the class

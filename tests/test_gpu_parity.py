@@ -78,6 +78,44 @@ def test_catalogue3_objectives_match_reference(sb):
     assert not bad, bad
 
 
+def test_rng_in_objective_classes(sb):
+    """Stochastic (go_funcs_S.py:1274-1280) and XinSheYang01 (go_funcs_X.py:47-51) draw U[0,1) factors
+    from NumPy's global generator inside fun(); the device functors take them from Philox noise
+    addressed by the point (sda_objectives_cat.cuh).  Checked: (i) values equal the integer
+    restatement oracle/rng_objectives.py to 1e-12; (ii) f(global optimum) == fglob exactly, as in the
+    reference where every term vanishes; (iii) the factors seen at 20,000 distinct points follow the
+    reference's law U[0,1) (Kolmogorov-Smirnov) and neighbouring points (1 ulp apart) get
+    uncorrelated factors -- what the finite-difference gradient of the reference observes."""
+    from scipy.stats import kstest
+    from oracle import rng_objectives as ro
+    rng = np.random.RandomState(7)
+    for name in ("Stochastic", "XinSheYang01"):
+        for dim in (2, 5, 10):
+            f = sb.DeviceFunctor(name, dimensions=dim)
+            X = rng.uniform(-5.0, 5.0, size=(24, dim))
+            F = f(X)
+            ref = np.array([ro.fun(name, x) for x in X])
+            assert np.all(np.abs(F - ref) <= 1e-12 * np.maximum(np.abs(ref), 1.0)), (name, dim, F, ref)
+            opt = 1.0 / np.arange(1, dim + 1) if name == "Stochastic" else np.zeros(dim)
+            assert f(opt) == 0.0 == f.fglob
+    n = 20000
+    f = sb.DeviceFunctor("Stochastic", dimensions=2)
+    X = np.column_stack([rng.uniform(-5.0, 0.0, n), np.full(n, 0.5)])   # second term vanishes
+    eps0 = f(X) / np.abs(X[:, 0] - 1.0)
+    assert eps0.min() >= 0.0 and eps0.max() < 1.0 + 1e-12
+    assert kstest(eps0, "uniform").pvalue > 1e-3
+    Xn = X.copy()
+    Xn[:, 0] = np.nextafter(X[:, 0], 0.0)
+    eps0n = f(Xn) / np.abs(Xn[:, 0] - 1.0)
+    assert abs(np.corrcoef(eps0, eps0n)[0, 1]) < 0.03
+    X1 = np.column_stack([np.ones(n), rng.uniform(1.0, 5.0, n)])        # first term vanishes
+    eps1 = f(X1) / np.abs(X1[:, 1] - 0.5)
+    assert kstest(eps1, "uniform").pvalue > 1e-3
+    g = sb.DeviceFunctor("XinSheYang01", dimensions=2)
+    Y = np.column_stack([rng.uniform(0.5, 5.0, n), np.zeros(n)])
+    assert kstest(g(Y) / Y[:, 0], "uniform").pvalue > 1e-3
+
+
 def test_device_math_accuracy(sb):
     """csrc/sda_math.cuh against x87 long double: log_pos and exp_any within 1.5 ulp, cos_2pi within
     4e-16 absolute of cos(2 pi x) (exact-period reduction; what `x^2 - 10 cos(2 pi x)` needs)."""
@@ -514,6 +552,7 @@ def test_suite_statistics_match_reference_whole_catalogue(sb):
     z = load_golden("suite_stats_ref_full.npz")
     budget, n = int(z["budget"]), int(z["nb_runs"])
     assert len(z["rows"]) >= 80
+    assert {"Stochastic", "XinSheYang01"} <= {str(r["job"]) for r in z["rows"]}
     seeds = np.arange(n, dtype=np.uint64) + np.uint64(1234)
     differ = []
     for r in z["rows"]:
