@@ -312,7 +312,7 @@ def run_ours(args):
                     "hbm_note": "chain state lives in shared memory; compulsory HBM traffic is "
                                 "(2D+6)*8 B per chain per run plus the L-BFGS-B slots (L2 resident)"}
         cpu = None
-        if world == 1 or True:
+        if world == 1:             # reported on rank 0 at N = 1 only (the reference arm covers every N)
             cores = os.cpu_count() or 1
             n = max(cores, 8) * 8
             ce, cdt, _ = cpu_reference_run(n, cores, args.maxiter, args.pure_sa)

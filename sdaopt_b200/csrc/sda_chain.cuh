@@ -79,9 +79,11 @@ template <bool INLINE_EVAL>
 __device__ __forceinline__ double call_func(const DeviceArgs &a, ChainState &st, const double *x,
                                             const Group &g)
 {
-    const double res = INLINE_EVAL ? eval_objective(a.functor, x, a.dim, a.params, g)
+    // salt: the call number, used only by the objectives that draw random numbers inside fun()
+    const unsigned long long salt = (unsigned long long)st.ncall;
+    const double res = INLINE_EVAL ? eval_objective(a.functor, x, a.dim, a.params, g, salt)
                                    : eval_objective_ool(a.functor, x, a.dim, a.params, g.G,
-                                                        g.gid * g.G + g.gl);
+                                                        g.gid * g.G + g.gl, salt);
     if (a.max_calls > 0 && !st.stop) {
         st.mon_calls += 1;                              // bench.py:300
         if (st.mon_calls >= a.max_calls) {              // bench.py:301-304

@@ -903,7 +903,8 @@ __device__ __noinline__ bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st
         double x2 = xi - respl;
         if (x2 < lo[i]) { x2 = lo[i]; respl = xi - x2; }
         double fe = 0.0;
-        if (valid) fe = eval_objective_solo_ool(a.functor, xe, i, plus ? x1 : x2, n, a.params, lane);
+        if (valid) fe = eval_objective_solo_ool(a.functor, xe, i, plus ? x1 : x2, n, a.params, lane,
+                                                (unsigned long long)(st.ncall + 1 + e));
         if (a.max_calls > 0) {
             const unsigned budget = __ballot_sync(SDA_FULL_MASK, valid && (mc0 + e + 1 >= a.max_calls));
             const unsigned hits = __ballot_sync(SDA_FULL_MASK, valid && (fe <= a.fglob_tol));

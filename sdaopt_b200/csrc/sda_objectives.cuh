@@ -48,7 +48,8 @@ __device__ __forceinline__ double eval_sutton_chen(const XV &x, int dim, const G
 // x is anything indexable: a pointer into shared memory, or a PerturbedView of it.
 template <class XV>
 __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
-                                                 const double *params, const Group &g)
+                                                 const double *params, const Group &g,
+                                                 unsigned long long salt = 0)
 {
     const int lane = g.gl, SDA_STRIDE = g.G;
     double a = 0.0, b = 0.0;
@@ -261,7 +262,7 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
         return ::sda_user_objective(x, dim, params);
 #endif
     default:  // ids 60..: the rest of the catalogue, out of line (cold code)
-        return eval_catalogue(fid, x, dim, g);
+        return eval_catalogue(fid, x, dim, g, salt);
     }
 }
 
@@ -278,19 +279,20 @@ struct PerturbedView {
 // registered objectives is ~4.5 K instructions, and inlining it at every call site grew the
 // L-BFGS-B code to 750 KB -- ncu showed 85 % of its cycles stalled on instruction fetch.
 __device__ __noinline__ double eval_objective_ool(int fid, const double *x, int dim,
-                                                  const double *params, int G, int lane)
+                                                  const double *params, int G, int lane,
+                                                  unsigned long long salt)
 {
-    return eval_objective(fid, x, dim, params, make_group(G, lane));
+    return eval_objective(fid, x, dim, params, make_group(G, lane), salt);
 }
 
 // One lane evaluates one perturbed point by itself (G = 1): the 2*D finite-difference evaluations
 // of a gradient run 32 at a time.
 __device__ __noinline__ double eval_objective_solo_ool(int fid, const double *x, int index,
                                                        double value, int dim, const double *params,
-                                                       int lane)
+                                                       int lane, unsigned long long salt)
 {
     const PerturbedView v = { x, index, value };
-    return eval_objective(fid, v, dim, params, make_group(1, lane));
+    return eval_objective(fid, v, dim, params, make_group(1, lane), salt);
 }
 
 }  // namespace sda

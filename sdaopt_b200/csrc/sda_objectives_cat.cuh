@@ -27,12 +27,15 @@ __device__ __forceinline__ double nan_value() { return __longlong_as_double(0x7f
 // ---- objectives that draw random numbers inside fun() --------------------------------------------
 // Stochastic (go_funcs_S.py:1274-1280) and XinSheYang01 (go_funcs_X.py:47-51) multiply every term by
 // eps_i ~ U[0,1) drawn from NumPy's GLOBAL generator at every call, so their value at a point is not
-// a function of the point and no call-by-call parity exists.  Here eps is counter-based noise
-// addressed by the point: Philox4x32-10 with counter (hash64(x), i, tag) -> the 53-bit uniform of
-// numpy's random_sample().  Every distinct point sees independent U[0,1) factors (what the chain,
-// the finite-difference gradient and the first-hit monitor observe in the reference), a repeated
-// request at a bit-identical point repeats its value (SciPy's ScalarFunction cache does the same),
-// and the evaluation needs no per-chain state.  Restated on the CPU in oracle/rng_objectives.py.
+// a function of the point and no call-by-call parity exists.  Here eps is counter-based noise:
+// Philox4x32-10 with counter (hash64(x) + salt * phi64, i) -> the 53-bit uniform of numpy's
+// random_sample().  `salt` is the chain's evaluation counter (ChainState::ncall; the 2 D points of
+// a gradient carry their own call numbers), so every call draws fresh factors exactly as in the
+// reference -- including repeated requests near one point, which is how the reference's line
+// searches eventually hit f <= 1e-8 on these functions: with noise addressed by the point alone the
+// reference itself drops from 29 % to 0 % success on Stochastic (measured, oracle/gen_suite_ref_rng.py
+// header).  sda_eval passes salt = 0: a pure function of the point, restated on the CPU in
+// oracle/rng_objectives.py.  Runs stay reproducible: the noise is a function of (x, call number).
 __device__ __forceinline__ uint64_t mix64(uint64_t z)     // splitmix64 finaliser
 {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -40,9 +43,9 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z)     // splitmix64 finalise
     return z ^ (z >> 31);
 }
 template <class XV>
-__device__ __forceinline__ uint64_t point_hash(const XV &x, int dim, const Group &g)
+__device__ __forceinline__ uint64_t point_hash(const XV &x, int dim, const Group &g, uint64_t salt)
 {
-    uint64_t h = 0;
+    uint64_t h = g.gl == 0 ? salt * 0x9E3779B97F4A7C15ull : 0ull;
     for (int k = g.gl; k < dim; k += g.G)
         h += mix64((uint64_t)__double_as_longlong(x[k]) + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ull);
     for (int o = g.G >> 1; o > 0; o >>= 1) h += __shfl_xor_sync(g.mask, h, o);
@@ -168,7 +171,8 @@ __device__ __forceinline__ double levy_chain(const XV &x, int dim, double c, con
 }
 
 template <class XV>
-__device__ __noinline__ double eval_catalogue(int fid, const XV &x, int dim, const Group &g)
+__device__ __noinline__ double eval_catalogue(int fid, const XV &x, int dim, const Group &g,
+                                             unsigned long long salt)
 {
     const int lane = g.gl, S = g.G;
     double a = 0.0, b = 0.0, c = 0.0;
@@ -835,12 +839,12 @@ __device__ __noinline__ double eval_catalogue(int fid, const XV &x, int dim, con
         return v;
     }
     case SDA_FN_STOCHASTIC: {  // sum(rnd * abs(x - 1/i)), i = 1..N
-        const uint64_t h = point_hash(x, dim, g);
+        const uint64_t h = point_hash(x, dim, g, salt);
         for (int k = lane; k < dim; k += S) a += point_noise(h, k, 0x53544F43u) * fabs(x[k] - 1.0 / (double)(k + 1));
         return group_sum(a, g);
     }
     case SDA_FN_XIN_SHE_YANG01: {  // sum(rnd * abs(x) ** i), i = 1..N
-        const uint64_t h = point_hash(x, dim, g);
+        const uint64_t h = point_hash(x, dim, g, salt);
         for (int k = lane; k < dim; k += S) a += point_noise(h, k, 0x58535931u) * pow(fabs(x[k]), (double)(k + 1));
         return group_sum(a, g);
     }

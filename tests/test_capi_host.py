@@ -57,6 +57,9 @@ def test_rng_objective_restatement_is_uniform_and_vanishes_at_the_optimum():
     epsn = np.array([ro.noise(x, "Stochastic") for x in Xn])
     assert abs(np.corrcoef(eps[:, 0], epsn[:, 0])[0, 1]) < 0.1
     assert abs(np.corrcoef(eps[:, 0], np.array([ro.noise(x, "XinSheYang01")[0] for x in X]))[0, 1]) < 0.1
+    # the call number re-draws the factors at the same point (fresh noise per call, as the reference)
+    e1 = np.array([ro.noise(X[0], "Stochastic", salt=s)[0] for s in range(1, 1501)])
+    assert kstest(e1, "uniform").pvalue > 1e-3 and len(np.unique(e1)) == 1500
     assert ro.fun("Stochastic", 1.0 / np.arange(1, 6)) == 0.0
     assert ro.fun("XinSheYang01", np.zeros(5)) == 0.0
     x = np.array([2.0, -3.0])

@@ -81,8 +81,10 @@ def test_catalogue3_objectives_match_reference(sb):
 def test_rng_in_objective_classes(sb):
     """Stochastic (go_funcs_S.py:1274-1280) and XinSheYang01 (go_funcs_X.py:47-51) draw U[0,1) factors
     from NumPy's global generator inside fun(); the device functors take them from Philox noise
-    addressed by the point (sda_objectives_cat.cuh).  Checked: (i) values equal the integer
-    restatement oracle/rng_objectives.py to 1e-12; (ii) f(global optimum) == fglob exactly, as in the
+    addressed by (point, call number) (sda_objectives_cat.cuh; sda_eval uses call number 0, chains
+    their evaluation counter -- the in-chain statistics are checked against the live reference by
+    test_suite_statistics_match_reference_whole_catalogue).  Checked here: (i) values equal the
+    integer restatement oracle/rng_objectives.py to 1e-12; (ii) f(global optimum) == fglob exactly, as in the
     reference where every term vanishes; (iii) the factors seen at 20,000 distinct points follow the
     reference's law U[0,1) (Kolmogorov-Smirnov) and neighbouring points (1 ulp apart) get
     uncorrelated factors -- what the finite-difference gradient of the reference observes."""
