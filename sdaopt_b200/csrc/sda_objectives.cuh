@@ -17,8 +17,29 @@
 
 namespace sda {
 
-// suttonchen.py:23-40  (A=1, C=39.432, M=6, K=9).  Lane L owns atoms L, L+32, ...: for each it
+// suttonchen.py:23-40  (A=1, C=39.432, M=6, K=9).  Lane L owns atoms L, L+G, ...: for each it
 // accumulates sum_j r_ij^-9 and sum_j r_ij^-6 over all other atoms from shared memory.
+// One pair term: r^-1 by rsqrt (1 ulp) instead of an IEEE division plus a square root, r^-6 and r^-9
+// by multiplication (relative error ~1e-15, inside the 1e-11 parity bound); the j == i term is
+// masked to zero instead of branched around, so that the four terms of a trip are independent
+// instruction streams.
+template <class XV>
+__device__ __forceinline__ void sutton_chen_term(const XV &x, int i, int j, double xi, double yi,
+                                                 double zi, double &rep, double &rho)
+{
+    const double dx = xi - x[3 * j], dy = yi - x[3 * j + 1], dz = zi - x[3 * j + 2];
+    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    const double inv1 = (j == i) ? 0.0 : rsqrt(r2);
+    const double inv2 = inv1 * inv1;
+    const double inv6 = inv2 * inv2 * inv2;
+    rho += inv6;
+    rep = fma(inv6 * inv2, inv1, rep);
+}
+
+// Four atoms j per trip with their own accumulators: at D = 3N >= 768 only 6-8 warps fit an SM
+// (the chain state lives in shared memory), and one dependent rsqrt/multiply chain per warp left the
+// FP64 pipe idle (ncu-less evidence: 67 G pair terms/s at N = 512 against 371 G at N = 128,
+// profiles/r1_config3_config4_shapes.log).
 template <class XV>
 __device__ __forceinline__ double eval_sutton_chen(const XV &x, int dim, const Group &g)
 {
@@ -26,19 +47,18 @@ __device__ __forceinline__ double eval_sutton_chen(const XV &x, int dim, const G
     double part = 0.0;
     for (int i = g.gl; i < n; i += g.G) {
         const double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
-        double rep = 0.0, rho = 0.0;
-        for (int j = 0; j < n; ++j) {
-            if (j == i) continue;
-            const double dx = xi - x[3 * j], dy = yi - x[3 * j + 1], dz = zi - x[3 * j + 2];
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            // r^-1 by rsqrt (1 ulp) instead of an IEEE division plus a square root: r^-6 and r^-9
-            // follow by multiplication (relative error ~1e-15, inside the 1e-11 parity bound)
-            const double inv1 = rsqrt(r2);
-            const double inv2 = inv1 * inv1;
-            const double inv6 = inv2 * inv2 * inv2;
-            rho += inv6;
-            rep += inv6 * inv2 * inv1;
+        double rep0 = 0.0, rho0 = 0.0, rep1 = 0.0, rho1 = 0.0;
+        double rep2 = 0.0, rho2 = 0.0, rep3 = 0.0, rho3 = 0.0;
+        int j = 0;
+        for (; j + 3 < n; j += 4) {
+            sutton_chen_term(x, i, j, xi, yi, zi, rep0, rho0);
+            sutton_chen_term(x, i, j + 1, xi, yi, zi, rep1, rho1);
+            sutton_chen_term(x, i, j + 2, xi, yi, zi, rep2, rho2);
+            sutton_chen_term(x, i, j + 3, xi, yi, zi, rep3, rho3);
         }
+        for (; j < n; ++j) sutton_chen_term(x, i, j, xi, yi, zi, rep0, rho0);
+        const double rep = (rep0 + rep1) + (rep2 + rep3);
+        const double rho = (rho0 + rho1) + (rho2 + rho3);
         part += 0.5 * rep - 39.432 * sqrt(rho);
     }
     return group_sum(part, g);
