@@ -553,7 +553,7 @@ def test_suite_statistics_match_reference_whole_catalogue(sb):
     from scipy.stats import fisher_exact, ks_2samp, mannwhitneyu
     z = load_golden("suite_stats_ref_full.npz")
     budget, n = int(z["budget"]), int(z["nb_runs"])
-    assert len(z["rows"]) >= 80
+    assert len(z["rows"]) >= 200
     assert {"Stochastic", "XinSheYang01"} <= {str(r["job"]) for r in z["rows"]}
     seeds = np.arange(n, dtype=np.uint64) + np.uint64(1234)
     differ = []
