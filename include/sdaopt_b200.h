@@ -332,6 +332,11 @@ const char *sda_last_cuda_error(void);
 /* functor id for a registered name ("Rastrigin", ...), or SDA_E_INVALID */
 int sda_functor_id(const char *name);
 const char *sda_functor_name(int functor);
+/* number of coordinates a fixed-arity catalogue class indexes (its `N` in go_funcs_*.py with
+ * change_dimensionality = False); 0 for the n-D classes; SDA_E_INVALID for an unknown id.  Every entry
+ * point rejects (SDA_E_INVALID) a problem whose dim differs from a non-zero arity -- the reference's
+ * fun() would raise IndexError there. */
+int sda_functor_arity(int functor);
 /* 1 if this build contains a user functor (SDA_FN_USER), else 0 */
 int sda_has_user_functor(void);
 /* number of CUDA devices visible, or SDA_E_CUDA */
@@ -395,6 +400,16 @@ int sda_visit_fn_host(double qv, double sigmax, const double *tape, int64_t tape
  * (:325-345).  success[i] mirrors mres.success; nfev[i] counts objective calls. */
 int sda_local_search_host(const SdaProblem *p, const double *x_in, int64_t n, double *x_out,
                           double *f_out, int32_t *success, int64_t *nfev, int device);
+
+/* EnergyState.reset(owf, rs, x0) (_sda.py:135-166) driven by a tape of uniforms: (re)initial location
+ * (x0 or lower + u*(upper-lower)), its energy through owf.func, up to 1000 re-draws while the energy
+ * is >= 1e16 or NaN (*status = SDA_CHAIN_REINIT_FAILED after that: the ValueError of :149-156), best
+ * retained when have_best != 0 (in: xbest[dim], *ebest) and set on the first evaluation otherwise
+ * (:163-165).  *tape_used = uniforms consumed, -1 if the tape was too short. */
+int sda_energy_reset_host(const SdaProblem *p, const double *x0, const double *tape, int64_t tape_len,
+                          int32_t have_best, double *current_location, double *current_energy,
+                          double *xbest, double *ebest, int32_t *status, int64_t *tape_used,
+                          int device);
 
 /* ---- measurement helper: sustained FP64 FMA rate of the device (roofline denominator) ----------- */
 int sda_fp64_peak(double *tflops, double *ms, int device);

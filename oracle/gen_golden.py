@@ -210,6 +210,75 @@ def gen_lbfgsb():
     print("lbfgsb cases", len(rows))
 
 
+def gen_lbfgsb_large():
+    """The same at the dimensions of BASELINE config 3 (D = 100 and D = 1000), where the device
+    keeps the L-BFGS-B workspace in global memory instead of shared memory.  Only the first request
+    points are stored (a D = 1000 case makes a few hundred requests of 1000 doubles each)."""
+    rows = []
+    for name, D, n_cases in [("Rastrigin", 100, 3), ("Ackley01", 100, 3), ("Schwefel26", 100, 3),
+                             ("Rastrigin", 1000, 2), ("Ackley01", 1000, 2), ("Schwefel26", 1000, 2)]:
+        k = getattr(gbf, name)(dimensions=D)
+        lo = np.array([b[0] for b in k.bounds], dtype=float)
+        up = np.array([b[1] for b in k.bounds], dtype=float)
+        rs = np.random.RandomState(70 + D)
+        for t in range(n_cases):
+            x0 = lo + rs.random_sample(D) * (up - lo)
+            if t == 0:
+                x0 = np.clip(np.array(k.global_optimum[0], dtype=float) + rs.normal(size=D) * 0.3,
+                             lo, up)
+            if t == 2:
+                x0[0] = lo[0]
+                x0[-1] = up[-1]          # start on the box
+            pts = []
+
+            def f(x, _p=pts, _k=k):
+                _p.append(np.array(x))
+                return _k.fun(x)
+            owf = R.ObjectiveFunWrapper(k.bounds, f)
+            e, x = owf.local_search(x0)
+            req = pts[::2 * D + 1]
+            rows.append(dict(functor=name, dim=D, bounds=np.array(k.bounds, dtype=float), x0=x0,
+                             success=x is not None, f=float(e),
+                             x=np.array(x0 if x is None else x), nfev=owf.nb_fun_call,
+                             n_requests=len(req), request_points=np.array(req[:4])))
+            print("lbfgsb large", name, D, t, "success", x is not None, "f", float(e), "nfev",
+                  owf.nb_fun_call, flush=True)
+    np.savez_compressed(os.path.join(GOLD, "lbfgsb_scipy_large.npz"), rows=np.array(rows, dtype=object),
+                        scipy_version=scipy.__version__)
+
+
+def gen_sutton_chen_traj():
+    """BASELINE config 4 at the size the reference defines (suttonchen.py:55-62: 6 atoms, bounds
+    +-0.7): the reference's own run on a recorded tape, pure SA -- energies and decisions of every
+    evaluation -- plus a 13-atom cluster in the constant-density box 0.7 (N/6)^(1/3)."""
+    for n_atoms, maxiter, seed in [(6, 80, 21), (13, 30, 22)]:
+        L = 0.7 * (n_atoms / 6.0) ** (1.0 / 3.0)
+        bounds = [(-L, L)] * (3 * n_atoms)
+        r = record_run(suttonchen.sutton_chen, None, bounds, seed, maxiter, True)
+        T, S = k1_tables(maxiter)
+        np.savez_compressed(os.path.join(GOLD, "traj_SuttonChen_n%d.npz" % n_atoms), functor="SuttonChen",
+                            params=[], bounds=np.array(bounds, dtype=float), seed=seed, maxiter=maxiter,
+                            temp_table=T, sigmax_table=S, **r)
+        print("traj SuttonChen", n_atoms, "fun", r["fun"], "ncall", r["ncall"], "tape", r["tape_len"])
+
+
+def gen_maxfun_anchor():
+    """maxfun only breaks the inner loop, the run still makes maxiter attempts."""
+    rows = []
+    for name, D, maxfun, maxiter, seed in [("Rastrigin", 2, 100, 200, 1234), ("Rastrigin", 5, 1000, 150, 3),
+                                           ("Rosenbrock", 2, 100, 200, 1234)]:
+        k = getattr(gbf, name)(dimensions=D)
+        ret = R.sda(k.fun, None, k.bounds, maxiter=maxiter, maxfun=maxfun, seed=seed, pure_sa=True)
+        ret_ls = R.sda(k.fun, None, k.bounds, maxiter=maxiter, maxfun=maxfun, seed=seed)
+        rows.append(dict(functor=name, dim=D, maxfun=maxfun, maxiter=maxiter, seed=seed,
+                         nit=int(ret.nit), ncall=int(ret.ncall), fun=float(ret.fun),
+                         nit_ls=int(ret_ls.nit), ncall_ls=int(ret_ls.ncall), fun_ls=float(ret_ls.fun),
+                         bounds=np.array(k.bounds, dtype=float)))
+        print("maxfun", name, D, maxfun, maxiter, "pure_sa nit/ncall", ret.nit, ret.ncall,
+              "with LS", ret_ls.nit, ret_ls.ncall)
+    np.savez_compressed(os.path.join(GOLD, "maxfun_anchor.npz"), rows=np.array(rows, dtype=object))
+
+
 def gen_objective_points():
     rows = []
     rs = np.random.RandomState(2024)
@@ -402,6 +471,10 @@ if __name__ == "__main__":
         gen_objective_points_cat3()
     elif MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "suite_stats":
         gen_suite_stats()
+    elif MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "round2":
+        gen_lbfgsb_large()
+        gen_sutton_chen_traj()
+        gen_maxfun_anchor()
     elif os.environ.get("SDA_GOLDEN_ONLY"):
         pass
     elif MODE == "libm":
@@ -411,6 +484,9 @@ if __name__ == "__main__":
         gen_trajectories()
         gen_ls_runs()
         gen_lbfgsb()
+        gen_lbfgsb_large()
+        gen_sutton_chen_traj()
+        gen_maxfun_anchor()
         gen_suite()
         gen_suite_stats()
     else:

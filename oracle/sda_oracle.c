@@ -560,7 +560,16 @@ static int energy_reset(Chain *ch, const double *x0)
     for (;;) {
         int done = 0;
         ch->e_cur = call_func(ch, ch->x_cur);   /* owf.func: NOT counted, _sda.py:144 */
-        if (ch->stop) return 0;
+        if (ch->stop) {
+            /* the suite monitor ended the run at its first evaluation (the reference leaves sda()
+             * through the monitor's exception): report that point */
+            if (!ch->have_best) {
+                ch->ebest = ch->e_cur;
+                memcpy(ch->xbest, ch->x_cur, sizeof(double) * ch->dim);
+                ch->have_best = 1;
+            }
+            return 0;
+        }
         if (ch->e_cur >= BIG_VALUE || isnan(ch->e_cur)) {
             if (reinit_counter >= MAX_REINIT_COUNT) return ORC_ERR_REINIT;
             draw_location(ch, attempt++);

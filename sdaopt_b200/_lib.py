@@ -19,7 +19,7 @@ EXPORTS = ["sda_abi_version", "sda_has_user_functor", "sda_error_string", "sda_l
            "sda_functor_name", "sda_device_count", "sda_workspace_bytes", "sda_batch_run", "sda_last_launch_count",
            "sda_batch_run_host", "sda_eval", "sda_eval_host", "sda_visiting_host",
            "sda_visit_fn_host", "sda_local_search_host", "sda_fp64_peak", "sda_kernel_timing",
-           "sda_kernel_times", "sda_math_probe_host"]
+           "sda_kernel_times", "sda_math_probe_host", "sda_functor_arity", "sda_energy_reset_host"]
 
 
 class SdaProblem(C.Structure):
@@ -112,6 +112,13 @@ def lib(path=None):
         L.sda_kernel_timing.argtypes = [C.c_int]
         L.sda_math_probe_host.restype = C.c_int
         L.sda_math_probe_host.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+        L.sda_functor_arity.restype = C.c_int
+        L.sda_functor_arity.argtypes = [C.c_int]
+        L.sda_energy_reset_host.restype = C.c_int
+        L.sda_energy_reset_host.argtypes = [C.POINTER(SdaProblem), C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
+                                            C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int64), C.c_int]
         L.sda_kernel_times.restype = C.c_int
         L.sda_kernel_times.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         if L.sda_abi_version() != 1:

@@ -116,8 +116,8 @@ def sda_batch(func, bounds, n_chains, x0=None, seeds=None, tape=None, maxiter=10
     if tape is not None:
         tape = np.ascontiguousarray(tape, dtype=np.float64).reshape(n_chains, -1)
         tape_len = tape.shape[1]
-    _lib.require_cuda()
     problem, keep = _functors.make_problem(functor, lower, upper)
+    _lib.require_cuda()
     tables = temperature_tables(maxiter, initial_temp, visit, 0.1)
     cfg = _make_config(maxiter, initial_temp, visit, accept, maxfun, pure_sa,
                        _lib.RNG_TAPE if tape is not None else _lib.RNG_PHILOX, max_calls, fglob,
@@ -243,7 +243,10 @@ class ObjectiveFunWrapper(object):
         self.func = _functors.resolve(func)
         self.nb_fun_call = 0
         self.kwargs = kwargs
-        unsupported = set(kwargs) - {'method', 'options', 'bounds', 'jac', 'eps'}
+        # the kernel runs exactly the reference's default minimiser (method L-BFGS-B, jac =
+        # self.gradient with eps = 1e-6, bounds = the search box, option dict :300-311); a kwarg that
+        # would change any of that cannot be honoured on the device, so it is refused, not ignored
+        unsupported = set(kwargs) - {'method'}
         if unsupported or kwargs.get('method', 'L-BFGS-B') != 'L-BFGS-B':
             raise NotImplementedError(
                 "sdaopt_b200 runs the reference's default local search (L-BFGS-B with the option "
@@ -277,50 +280,47 @@ class ObjectiveFunWrapper(object):
         return float(fo[0]), xo[0]
 
 
-class EnergyState():
-    """Current / best location and energy with the (re)initialisation rule (:110-166)."""
+class EnergyState(object):
+    """The reference's ``EnergyState`` (:110-166) as a host handle on device state.
+
+    ``reset`` runs the (re)initialisation rule on the GPU (``sda_energy_reset_host``: the same
+    ``energy_reset`` device function the annealing kernels call at chain start and on re-annealing)
+    with the uniforms of ``rs`` injected in the reference's draw order, then advances ``rs`` by the
+    number of uniforms the kernel consumed.  Attributes mirror the reference's: ``current_location``,
+    ``current_energy``, ``xbest``, ``ebest`` (the best is kept across resets, :163-165)."""
     MAX_REINIT_COUNT = 1000
 
     def __init__(self, lower, upper):
-        self.ebest = None
-        self.current_energy = None
-        self.current_location = None
-        self.xbest = None
-        self.lower = lower
-        self.upper = upper
+        self.lower = np.ascontiguousarray(lower, dtype=np.float64)
+        self.upper = np.ascontiguousarray(upper, dtype=np.float64)
+        self.current_location = self.current_energy = self.xbest = self.ebest = None
 
-    def reset(self, owf, rs, x0=None):
-        """:135-166 (host orchestration of device evaluations; the batched path runs the same
-        rule inside the kernel)."""
-        if x0 is None:
-            self.current_location = self.lower + rs.random_sample(
-                len(self.lower)) * (self.upper - self.lower)
-        else:
-            self.current_location = np.copy(x0)
-        init_error = True
-        reinit_counter = 0
-        while init_error:
-            self.current_energy = owf.func(self.current_location)
-            if self.current_energy is None:
-                raise ValueError('Objective function is returning None')
-            if (self.current_energy >= BIG_VALUE or
-                    np.isnan(self.current_energy)):
-                if reinit_counter >= EnergyState.MAX_REINIT_COUNT:
-                    init_error = False
-                    message = (
-                        'Stopping algorithm because function '
-                        'create NaN or (+/-) inifinity values even with '
-                        'trying new random parameters'
-                    )
-                    raise ValueError(message)
-                self.current_location = self.lower + rs.random_sample(
-                    self.lower.size) * (self.upper - self.lower)
-                reinit_counter += 1
-            else:
-                init_error = False
-            if self.ebest is None and self.xbest is None:
-                self.ebest = self.current_energy
-                self.xbest = np.copy(self.current_location)
+    def reset(self, owf, rs, x0=None, device=0):
+        functor = owf.func if isinstance(owf, ObjectiveFunWrapper) else _functors.resolve(owf)
+        dim = self.lower.size
+        start = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        if start is not None and start.size != dim:
+            raise ValueError('Bounds size does not match x0')
+        problem, keep = _functors.make_problem(functor, self.lower, self.upper)
+        have_best = self.ebest is not None
+        _lib.require_cuda()
+
+        def fn(tape):
+            loc, best = np.empty(dim), np.zeros(dim)
+            if have_best:
+                best[:] = self.xbest
+            e, eb = C.c_double(), C.c_double(self.ebest if have_best else 0.0)
+            status, used = C.c_int32(), C.c_int64()
+            _lib.check(_lib.lib(functor.library_path).sda_energy_reset_host(
+                C.byref(problem), _ptr(start), tape.ctypes.data, tape.size, int(have_best),
+                loc.ctypes.data, C.byref(e), best.ctypes.data, C.byref(eb), C.byref(status),
+                C.byref(used), int(device)))
+            return used.value, (loc, e.value, best, eb.value, status.value)
+
+        (loc, e, best, eb, status), _ = _TapeFeeder(rs).run(4 * dim + 16, fn)
+        _raise_chain_errors(np.array([status]))
+        self.current_location, self.current_energy = loc, e
+        self.xbest, self.ebest = best, eb
 
 
 class SDARunner(object):

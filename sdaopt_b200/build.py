@@ -14,6 +14,17 @@ SOURCES = ["sda_kernels.cu"]
 HEADERS = ["sda_device.cuh", "sda_objectives.cuh", "sda_objectives_cat.cuh", "sda_math.cuh",
            "sda_chain.cuh", "sda_lbfgsb.cuh",
            os.path.join("..", "..", "include", "sdaopt_b200.h")]
+
+
+def _include_flags():
+    """-I for the C-ABI header: the repository's include/ in a checkout, a copy next to the sources
+    (csrc/sdaopt_b200.h, put there by setup.py) in an installed wheel."""
+    repo_inc = os.path.join(os.path.dirname(HERE), "include")
+    if os.path.exists(os.path.join(repo_inc, "sdaopt_b200.h")):
+        return ["-I", repo_inc]
+    if os.path.exists(os.path.join(CSRC, "sdaopt_b200.h")):
+        return ["-I", CSRC]
+    raise RuntimeError("sdaopt_b200.h not found (include/ of the checkout or csrc/ of the wheel)")
 # --fmad=false: no implicit FMA contraction, so objective values round like the reference's numpy
 # expressions and the oracle's -ffp-contract=off C (e.g. Bukin06 at its optimum (-10, 1):
 # x1 - 0.01*x0^2 is exactly 0 in the reference, 4.6e-7 after sqrt with a contracted fma).  libdevice
@@ -46,7 +57,7 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     extra = os.environ.get("SDA_NVCC_EXTRA", "").split()
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [_nvcc()] + NVCC_FLAGS + _include_flags() + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return LIB
@@ -54,7 +65,7 @@ def build(force=False, verbose=False):
 
 def build_user(header_path, out_path):
     """The same library with a user-supplied device functor compiled in as SDA_FN_USER."""
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-DSDA_USER_FUNCTOR_HEADER="%s"' % os.path.abspath(header_path),
+    cmd = [_nvcc()] + NVCC_FLAGS + _include_flags() + ['-DSDA_USER_FUNCTOR_HEADER="%s"' % os.path.abspath(header_path),
                                     "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return out_path

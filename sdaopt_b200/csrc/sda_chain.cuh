@@ -155,7 +155,16 @@ __device__ __noinline__ int energy_reset(const DeviceArgs &a, ChainState &st, Rn
     for (;;) {
         bool done = false;
         st.e_cur = call_func<false>(a, st, x_cur, g);   // owf.func: not counted      :144
-        if (st.stop) return 0;
+        if (st.stop) {
+            // the suite monitor ended the run at its very first evaluation (the reference leaves
+            // sda() through the monitor's exception here): report that point, not stale memory
+            if (!st.have_best) {
+                st.ebest = st.e_cur;
+                copy_vec(xbest, x_cur, dim, g);
+                st.have_best = 1;
+            }
+            return 0;
+        }
         if (st.e_cur >= kBigValue || isnan(st.e_cur)) {
             if (reinit >= kMaxReinit) return SDA_CHAIN_REINIT_FAILED;
             draw_location<TAPE>(rng, x_cur, bx, dim, attempt++, g);

@@ -11,7 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/sdaopt_b200.h"
+#include "sdaopt_b200.h"   // include/sdaopt_b200.h (-I include; shipped next to csrc/ in a wheel)
 #include "sda_math.cuh"
 
 #define SDA_WARP 32

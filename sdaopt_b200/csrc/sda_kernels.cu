@@ -603,6 +603,38 @@ __global__ void __launch_bounds__(128) sda_local_search_kernel(DeviceArgs a, con
     }
 }
 
+// EnergyState.reset on a tape, one warp (unit-test hook)                            :135-166
+// scal: [0] current_energy, [1] ebest (in: the retained best when have_best, out: the best after)
+__global__ void sda_energy_reset_kernel(DeviceArgs a, const double *x0, int have_best, double *x_cur_out,
+                                        double *xbest_io, double *scal, int *status, long long *tape_used)
+{
+    extern __shared__ double smem[];
+    const int dim = a.dim, lane = threadIdx.x & 31;
+    const Group g = make_group(SDA_WARP, lane);
+    double *lo = smem, *up = smem + dim, *rg = smem + 2 * dim, *irg = smem + 3 * dim, *x_cur = smem + 4 * dim;
+    for (int k = lane; k < dim; k += SDA_WARP) {
+        const double l = a.lower[k], u = a.upper[k];
+        lo[k] = l; up[k] = u; rg[k] = __dsub_rn(u, l); irg[k] = __ddiv_rn(1.0, rg[k]);
+    }
+    __syncwarp();
+    const Box bx = { lo, up, rg, irg };
+    ChainState st;
+    memset(&st, 0, sizeof(st));
+    st.have_best = have_best;
+    st.ebest = scal[1];
+    Rng<true> rng;
+    rng.t.tape = a.tape; rng.t.pos = 0; rng.t.len = a.tape_len; rng.t.exhausted = false;
+    const int err = energy_reset<true>(a, st, rng, x_cur, bx, x0, xbest_io, g);
+    __syncwarp();
+    for (int k = lane; k < dim; k += SDA_WARP) x_cur_out[k] = x_cur[k];
+    if (lane == 0) {
+        scal[0] = st.e_cur;
+        scal[1] = st.ebest;
+        *status = err;
+        *tape_used = rng.t.exhausted ? -1 : rng.t.pos;
+    }
+}
+
 // accuracy probe of sda_math.cuh
 __global__ void sda_math_probe_kernel(int kind, const double *x, long long n, double *out)
 {
@@ -688,6 +720,50 @@ static bool functor_ok(int f)
 {
     if (f >= 0 && f < SDA_FN_COUNT) return true;
     return f == SDA_FN_USER && sda_has_user_functor();
+}
+
+// Arity of the catalogue classes whose fun() indexes x[0..N-1] unconditionally (their `N` in
+// go_benchmark_functions/go_funcs_*.py with change_dimensionality = False); 0 = any dimension.
+// The reference raises IndexError (or silently ignores extra coordinates) for a wrong-sized x; here a
+// mismatch would read past the chain's shared-memory row, so it is rejected up front.
+static const unsigned char kFunctorArity[SDA_FN_COUNT] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2,
+    2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 0, 0, 0, 0, 0, 0, 0, 2, 0, 2,
+    0, 0, 2, 2, 3, 4, 5, 2, 2, 3, 2, 2, 2, 2, 2, 2, 17, 4, 4, 2, 2, 2, 0, 2, 4, 5, 0, 2, 0, 2,
+    0, 5, 3, 0, 2, 2, 2, 4, 2, 3, 2, 3, 6, 3, 2, 2, 0, 2, 2, 0, 2, 4, 2, 0, 2, 2, 3, 2, 4, 0,
+    0, 2, 2, 2, 2, 0, 2, 3, 2, 0, 0, 0, 2, 2, 2, 2, 10, 2, 0, 0, 0, 0, 0, 4, 4, 2, 2, 2, 0, 4,
+    3, 2, 2, 2, 2, 2, 0, 2, 2, 2, 0, 0, 2, 2, 4, 4, 4, 0, 0, 0, 0, 2, 7, 2, 2, 0, 2, 2, 2, 2,
+    2, 2, 0, 6, 2, 2, 0, 0, 3, 0, 0, 9, 0, 0, 0, 2, 0, 0,
+};
+
+extern "C" int sda_functor_arity(int functor)
+{
+    if (functor < 0 || functor >= SDA_FN_COUNT) return SDA_E_INVALID;
+    return kFunctorArity[functor];
+}
+
+// functor id known, dimension admissible for it
+static bool problem_shape_ok(int functor, int dim)
+{
+    if (!functor_ok(functor) || dim <= 0) return false;
+    if (functor == SDA_FN_USER) return true;
+    if (kFunctorArity[functor] && dim != kFunctorArity[functor]) return false;
+    if ((functor == SDA_FN_SUTTON_CHEN || functor == SDA_FN_LENNARD_JONES) && dim % 3 != 0) return false;
+    return true;
+}
+
+// SM count of the current device (cached per device ordinal)
+static int device_sms(void)
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+        cached[dev] = sms;
+    }
+    return cached[dev];
 }
 
 extern "C" const char *sda_error_string(int code)
@@ -776,7 +852,7 @@ static int pick_group(int dim, int rng_mode, long long n_chains)
     }
     int g = 1;
     while (g < 32 && (dim + g - 1) / g > 8) g <<= 1;
-    while (g < 32 && n_chains * (2LL * g) <= 32LL * 148 * 16) g <<= 1;
+    while (g < 32 && n_chains * (2LL * g) <= 32LL * device_sms() * 16) g <<= 1;
     return g;
 }
 
@@ -834,28 +910,32 @@ static int plan_launch(int dim, long long n_chains, int pure_sa, int group, int 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // workspace layout: [counter 256B][temp table][sigmax table][xmin C*D][ls slots]
-// parked-chain buffers of the phased execution
-static size_t g_off_recs, g_off_recx, g_off_rq, g_off_lq;   // set by workspace_layout (host, per call)
+//                   [parked-chain buffers of the phased execution: recs, rec_x, ready_q, ls_q]
+struct WsLayout {
+    size_t temp, sig, xmin, ls, recs, recx, rq, lq, total;
+    long long ls_stride;
+};
 
-static size_t workspace_layout(const SdaProblem *p, const SdaConfig *c, long long n_chains,
-                               long long slots, size_t *off_temp, size_t *off_sig, size_t *off_xmin,
-                               size_t *off_ls, long long *ls_stride)
+static WsLayout workspace_layout(const SdaProblem *p, const SdaConfig *c, long long n_chains, long long slots)
 {
+    WsLayout w;
+    memset(&w, 0, sizeof(w));
     const long long tn = table_entries(c);
     size_t off = 256;
-    *off_temp = off; off += align256((size_t)tn * sizeof(double));
-    *off_sig = off; off += align256((size_t)tn * sizeof(double));
-    *off_xmin = off; off += align256((size_t)n_chains * p->dim * sizeof(double));
-    *off_ls = off;
-    *ls_stride = (sda::ls_workspace_doubles(p->dim) + 31) & ~31LL;
+    w.temp = off; off += align256((size_t)tn * sizeof(double));
+    w.sig = off; off += align256((size_t)tn * sizeof(double));
+    w.xmin = off; off += align256((size_t)n_chains * p->dim * sizeof(double));
+    w.ls = off;
+    w.ls_stride = (sda::ls_workspace_doubles(p->dim) + 31) & ~31LL;
     if (!c->pure_sa) {
-        off += align256((size_t)slots * (size_t)*ls_stride * sizeof(double));
-        g_off_recs = off; off += align256((size_t)n_chains * sizeof(sda::ChainRec));
-        g_off_recx = off; off += align256((size_t)n_chains * p->dim * sizeof(double));
-        g_off_rq = off; off += align256((size_t)2 * n_chains * sizeof(int));
-        g_off_lq = off; off += align256((size_t)n_chains * sizeof(int));
+        off += align256((size_t)slots * (size_t)w.ls_stride * sizeof(double));
+        w.recs = off; off += align256((size_t)n_chains * sizeof(sda::ChainRec));
+        w.recx = off; off += align256((size_t)n_chains * p->dim * sizeof(double));
+        w.rq = off; off += align256((size_t)2 * n_chains * sizeof(int));
+        w.lq = off; off += align256((size_t)n_chains * sizeof(int));
     }
-    return off;
+    w.total = off;
+    return w;
 }
 
 // Phased execution (annealing launches alternating with local-search launches) is the default for
@@ -873,7 +953,7 @@ static bool use_phased(const SdaConfig *c, long long n_chains)
     // per warp to average the heavy-tailed search lengths: measured crossover for D=50 at ~12 k
     // chains (8 k: -11 %, 16 k: +16 %, 32 k: +43 %, 64 k: +35 %); Sutton-Chen N=38 with 8 k chains
     // is 5x slower phased.  148 SMs x 4 CTAs x 4 warps = 2368 searches run concurrently.
-    return n_chains >= 8LL * 148 * SDA_LS_MIN_BLOCKS * 4;
+    return n_chains >= 8LL * device_sms() * SDA_LS_MIN_BLOCKS * 4;
 }
 
 static thread_local long long g_last_launches = 0;
@@ -927,17 +1007,14 @@ static int max_slots(void)
 extern "C" size_t sda_workspace_bytes(const SdaProblem *p, const SdaConfig *c, int64_t n_chains)
 {
     if (!p || !c || p->dim <= 0 || n_chains <= 0) return 0;
-    size_t a, b, d, e;
-    long long s;
-    return workspace_layout(p, c, n_chains, max_slots(), &a, &b, &d, &e, &s);
+    return workspace_layout(p, c, n_chains, max_slots()).total;
 }
 
 static int validate(const SdaProblem *p, const SdaConfig *c, int64_t n_chains)
 {
     if (!p || !c || p->dim <= 0 || n_chains <= 0) return SDA_E_INVALID;
-    if (!functor_ok(p->functor)) return SDA_E_INVALID;
+    if (!problem_shape_ok(p->functor, p->dim)) return SDA_E_INVALID;
     if (c->rng_mode != SDA_RNG_PHILOX && c->rng_mode != SDA_RNG_TAPE) return SDA_E_INVALID;
-    if (p->functor == SDA_FN_SUTTON_CHEN && p->dim % 3 != 0) return SDA_E_INVALID;
     if ((p->functor == SDA_FN_SHIFTED_RASTRIGIN || p->functor == SDA_FN_CONSTANT) &&
         (p->params == NULL || p->n_params < 1))
         return SDA_E_INVALID;
@@ -963,12 +1040,11 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
                      (phased || (c->pure_sa && c->rng_mode != SDA_RNG_TAPE && group < 32)) ? SDA_PHASED_MIN_BLOCKS
                                                                                           : SDA_ANNEAL_MIN_BLOCKS, &lp);
     if (rc) return rc;
-    size_t off_temp, off_sig, off_xmin, off_ls;
-    long long ls_stride;
-    const size_t need = workspace_layout(p, c, n_chains, max_slots(), &off_temp, &off_sig, &off_xmin,
-                                         &off_ls, &ls_stride);
-    const size_t off_recs = g_off_recs, off_recx = g_off_recx, off_rq = g_off_rq, off_lq = g_off_lq;
-    if (need > workspace_bytes) return SDA_E_WORKSPACE;
+    const WsLayout wl = workspace_layout(p, c, n_chains, max_slots());
+    const size_t off_temp = wl.temp, off_sig = wl.sig, off_xmin = wl.xmin, off_ls = wl.ls;
+    const size_t off_recs = wl.recs, off_recx = wl.recx, off_rq = wl.rq, off_lq = wl.lq;
+    const long long ls_stride = wl.ls_stride;
+    if (wl.total > workspace_bytes) return SDA_E_WORKSPACE;
     char *ws = (char *)workspace;
 
     // K1 tables (host) -> device
@@ -1174,9 +1250,9 @@ extern "C" int sda_batch_run_host(const SdaProblem *p, const SdaConfig *c, int64
 extern "C" int sda_eval(const SdaProblem *p, const double *x, int64_t n, double *f, void *stream)
 {
     if (!p || !x || !f || n <= 0 || p->dim <= 0) return SDA_E_INVALID;
-    if (!functor_ok(p->functor)) return SDA_E_INVALID;
+    if (!problem_shape_ok(p->functor, p->dim)) return SDA_E_INVALID;
     long long blocks = (n + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > device_sms() * 8) blocks = device_sms() * 8;
     sda::sda_eval_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p->functor, p->dim, p->params, x, n, f,
                                                                        p->functor == SDA_FN_USER ? pick_group_user(p->dim) : pick_group(p->dim, SDA_RNG_PHILOX, 1LL << 40));
     CK(cudaGetLastError());
@@ -1186,6 +1262,7 @@ extern "C" int sda_eval(const SdaProblem *p, const double *x, int64_t n, double 
 extern "C" int sda_eval_host(const SdaProblem *p, const double *x, int64_t n, double *f, int device)
 {
     if (!p || !x || !f || n <= 0 || p->dim <= 0) return SDA_E_INVALID;
+    if (!problem_shape_ok(p->functor, p->dim)) return SDA_E_INVALID;
     CK(cudaSetDevice(device));
     DevBuf dx, df, pa;
     SdaProblem dp = *p;
@@ -1250,7 +1327,7 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
                                      int device)
 {
     if (!p || !x_in || !x_out || !f_out || n <= 0 || p->dim <= 0) return SDA_E_INVALID;
-    if (!functor_ok(p->functor)) return SDA_E_INVALID;
+    if (!problem_shape_ok(p->functor, p->dim)) return SDA_E_INVALID;
     CK(cudaSetDevice(device));
     DevBuf lo, up, pa, dxi, dxo, dfo, dsu, dnf, dls;
     SdaProblem dp;
@@ -1267,7 +1344,7 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
     while (wpb > 1 && (size_t)(2 + wpb) * D * 8 + wpb * lsb > (size_t)smem_max) wpb >>= 1;
     const size_t smem = (size_t)(2 + wpb) * D * 8 + wpb * lsb;
     long long blocks = (n + wpb - 1) / wpb;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > device_sms() * 4) blocks = device_sms() * 4;
     const long long stride = (sda::ls_workspace_doubles(p->dim) + 31) & ~31LL;
     CK(dls.alloc((size_t)blocks * wpb * (size_t)stride * 8));
     DeviceArgs a;
@@ -1287,6 +1364,51 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
     CK(cudaMemcpy(f_out, dfo.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (success) CK(cudaMemcpy(success, dsu.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     if (nfev) CK(cudaMemcpy(nfev, dnf.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SDA_OK;
+}
+
+extern "C" int sda_energy_reset_host(const SdaProblem *p, const double *x0, const double *tape,
+                                     int64_t tape_len, int32_t have_best, double *current_location,
+                                     double *current_energy, double *xbest, double *ebest,
+                                     int32_t *status, int64_t *tape_used, int device)
+{
+    if (!p || !tape || tape_len <= 0 || !current_location || !current_energy || !xbest || !ebest || !status)
+        return SDA_E_INVALID;
+    if (!problem_shape_ok(p->functor, p->dim)) return SDA_E_INVALID;
+    if ((p->functor == SDA_FN_SHIFTED_RASTRIGIN || p->functor == SDA_FN_CONSTANT) && (p->params == NULL || p->n_params < 1))
+        return SDA_E_INVALID;
+    CK(cudaSetDevice(device));
+    DevBuf lo, up, pa, dx0, dt, dxc, dxb, dsc, dst, dtu;
+    SdaProblem dp;
+    int rc = upload_problem(p, &dp, lo, up, pa);
+    if (rc) return rc;
+    const size_t D = (size_t)p->dim;
+    if (x0) CK(dx0.upload(x0, D * 8));
+    CK(dt.upload(tape, sizeof(double) * (size_t)tape_len));
+    CK(dxc.alloc(D * 8));
+    CK(dxb.upload(xbest, D * 8));
+    const double sc[2] = { 0.0, *ebest };
+    CK(dsc.upload(sc, sizeof(sc)));
+    CK(dst.alloc(4)); CK(dtu.alloc(8));
+    DeviceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.functor = p->functor; a.dim = p->dim; a.lower = dp.lower; a.upper = dp.upper; a.params = dp.params;
+    a.tape = (const double *)dt.p; a.tape_len = tape_len;
+    a.fglob_tol = nan("");
+    const size_t smem = 5 * D * sizeof(double);
+    CK(cudaFuncSetAttribute(sda::sda_energy_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sda::sda_energy_reset_kernel<<<1, 32, smem>>>(a, (const double *)dx0.p, have_best ? 1 : 0, (double *)dxc.p,
+                                                  (double *)dxb.p, (double *)dsc.p, (int *)dst.p, (long long *)dtu.p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    double sc_out[2];
+    CK(cudaMemcpy(sc_out, dsc.p, sizeof(sc_out), cudaMemcpyDeviceToHost));
+    *current_energy = sc_out[0];
+    *ebest = sc_out[1];
+    CK(cudaMemcpy(current_location, dxc.p, D * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(xbest, dxb.p, D * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(status, dst.p, 4, cudaMemcpyDeviceToHost));
+    if (tape_used) CK(cudaMemcpy(tape_used, dtu.p, 8, cudaMemcpyDeviceToHost));
     return SDA_OK;
 }
 

@@ -569,6 +569,11 @@ def make_problem(functor, lower, upper):
     lower = np.ascontiguousarray(lower, dtype=np.float64)
     upper = np.ascontiguousarray(upper, dtype=np.float64)
     params = functor.params
+    meta = _CATALOGUE_ALL.get(functor.name)
+    if meta is not None and not meta[1] and lower.size != meta[0]:
+        # fixed-arity class: its fun() indexes x[0..N-1] (the reference raises IndexError on a short x)
+        raise ValueError("%s is defined for exactly %d dimensions, got bounds of length %d"
+                         % (functor.name, meta[0], lower.size))
     p = _lib.SdaProblem(functor.functor_id, int(lower.size), lower.ctypes.data, upper.ctypes.data,
                         params.ctypes.data if params.size else None, int(params.size))
     return p, (lower, upper, params)

@@ -65,3 +65,30 @@ def gather_ragged(rec, dst=0):
         return None
     full = full.reshape(world, max(lens), rec.shape[1])
     return torch.cat([full[r, :lens[r]] for r in range(world)], dim=0)
+
+
+# ---- the suite's work list: (job, run) pairs, the runs of every job split over the ranks -----------
+SUITE_RECORD_COLS = ("job", "run", "hit", "ncall_hit", "f_hit", "device_ms")
+
+
+def suite_records(job_index, run_begin, hit, ncall_hit, f_hit, device_ms):
+    """[n_runs, 6] float64 rows of one job's runs [run_begin, run_begin + n) on this rank."""
+    n = len(hit)
+    k = np.arange(run_begin, run_begin + n, dtype=np.float64)
+    return np.stack([np.full(n, float(job_index)), k, np.asarray(hit, dtype=np.float64),
+                     np.asarray(ncall_hit, dtype=np.float64), np.asarray(f_hit, dtype=np.float64),
+                     np.full(n, float(device_ms))], axis=1)
+
+
+def assemble_suite_records(full, n_jobs, nbruns):
+    """Gathered rows of all ranks -> per job (hit[nbruns], ncall_hit, f_hit, device_ms max over
+    ranks), runs in index order.  Raises if a (job, run) pair is missing or duplicated."""
+    full = np.asarray(full, dtype=np.float64)
+    out = []
+    for j in range(n_jobs):
+        rows = full[full[:, 0] == j]
+        rows = rows[np.argsort(rows[:, 1], kind="stable")]
+        if rows.shape[0] != nbruns or not np.array_equal(rows[:, 1], np.arange(nbruns, dtype=np.float64)):
+            raise ValueError("suite records of job %d are incomplete: %d of %d runs" % (j, rows.shape[0], nbruns))
+        out.append((rows[:, 2] != 0, rows[:, 3], rows[:, 4], float(rows[:, 5].max())))
+    return out

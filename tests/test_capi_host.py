@@ -129,6 +129,36 @@ def test_argument_validation_mirrors_reference():
     assert sb.ObjectiveFunWrapper([(-1, 1)] * 500, "Sphere").ls_max_iter == 1000
 
 
+def test_fixed_arity_functors_reject_other_dimensions():
+    """Hartmann6, Thurber, ... index x[0..N-1] unconditionally (the reference raises IndexError on a
+    short x); a mismatch is refused on the host (ValueError) and by the library (SDA_E_INVALID)."""
+    import sdaopt_b200 as sb
+    from sdaopt_b200 import _lib, functors
+    L = _lib.lib()
+    for name, (n, nd, _box, _f) in functors._CATALOGUE_ALL.items():
+        assert L.sda_functor_arity(functors.FUNCTOR_IDS[name]) == (0 if nd else n), name
+    assert L.sda_functor_arity(0) == 0 and L.sda_functor_arity(9999) == _lib.SDA_E_INVALID
+    with pytest.raises(ValueError, match="exactly 6 dimensions"):
+        functors.make_problem(sb.DeviceFunctor("Hartmann6"), np.zeros(3), np.ones(3))
+    with pytest.raises(ValueError, match="exactly 6 dimensions"):
+        sb.sda_batch("Hartmann6", [(0, 1)] * 3, 4)
+    with pytest.raises(ValueError):
+        sb.DeviceFunctor("Thurber")(np.zeros((2, 5)))
+    # the library itself refuses too (a caller that bypasses the Python layer)
+    lo, up = np.zeros(3), np.ones(3)
+    p = _lib.SdaProblem(functors.FUNCTOR_IDS["Hartmann6"], 3, lo.ctypes.data, up.ctypes.data, None, 0)
+    cfg = _lib.SdaConfig(10, 5230., 2.62, -5.0, 1e7, 1, 0.1, 0, 0, float("nan"), 1e-8, 0, None, None, 0)
+    out = np.zeros(16)
+    res = _lib.SdaResult(*([out.ctypes.data] * 13))
+    assert L.sda_batch_run_host(C.byref(p), C.byref(cfg), 1, None, None, None, 0, C.byref(res), 0) == _lib.SDA_E_INVALID
+    assert L.sda_eval_host(C.byref(p), lo.ctypes.data, 1, out.ctypes.data, 0) == _lib.SDA_E_INVALID
+    # kwargs that would change the local minimiser are refused, not ignored (_sda.py:300-319)
+    for kw in ({"eps": 1e-4}, {"jac": True}, {"options": {"maxiter": 5}}, {"args": (1.0,)}):
+        with pytest.raises(NotImplementedError):
+            sb.ObjectiveFunWrapper([(-1, 1)] * 2, "Sphere", **kw)
+    assert sb.ObjectiveFunWrapper([(-1, 1)] * 2, "Sphere", method="L-BFGS-B").ls_max_iter == 100
+
+
 def test_functor_resolution():
     import sdaopt_b200 as sb
     from sdaopt_b200 import functors

@@ -37,6 +37,41 @@ def _worker(rank, world, port, n_total, out_path):
     dist.destroy_process_group()
 
 
+def _suite_worker(rank, world, port, n_jobs, nbruns, out_path):
+    """The suite's sharding as Benchmarker.run does it: every rank takes a slice of the runs of every
+    job, makes its records, rank 0 assembles them per job."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b, e = sharding.shard_range(nbruns, world, rank)
+    rows = []
+    for j in range(n_jobs):
+        keys = sharding.chain_keys(1234, b, e).astype(np.float64)
+        rows.append(sharding.suite_records(j, b, (keys + j) % 3 != 0, keys * 10 + j, keys * 0.25 - j, 100.0 * rank + j))
+    rec = torch.from_numpy(np.concatenate(rows, axis=0)) if rows and e > b else torch.zeros((0, 6), dtype=torch.float64)
+    full = sharding.gather_ragged(rec, dst=0)
+    if rank == 0:
+        torch.save(full, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_suite_run_sharding_assembles_every_job_run_pair(tmp_path):
+    n_jobs, nbruns = 7, 25                 # ragged: 12 + 13 runs per job
+    out = str(tmp_path / "suite.pt")
+    mp.spawn(_suite_worker, args=(2, _free_port(), n_jobs, nbruns, out), nprocs=2, join=True)
+    per_job = sharding.assemble_suite_records(torch.load(out).numpy(), n_jobs, nbruns)
+    keys = sharding.chain_keys(1234, 0, nbruns).astype(np.float64)
+    for j, (ok, ncall_hit, f_hit, ms) in enumerate(per_job):
+        np.testing.assert_array_equal(ok, (keys + j) % 3 != 0)        # run i keeps seed 1234 + i on any world size
+        np.testing.assert_array_equal(ncall_hit, keys * 10 + j)
+        np.testing.assert_array_equal(f_hit, keys * 0.25 - j)
+        assert ms == 100.0 + j                                         # max over the ranks
+    import pytest
+    with pytest.raises(ValueError):
+        sharding.assemble_suite_records(torch.load(out).numpy()[1:], n_jobs, nbruns)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
