@@ -247,6 +247,35 @@ def gen_lbfgsb_large():
                         scipy_version=scipy.__version__)
 
 
+def gen_lbfgsb_catalogue():
+    """The same for the catalogue classes whose suite statistics hinge on the local search's last
+    digits (success means f <= fglob + 1e-8 and L-BFGS-B stops on a 2.2e-9 decrease): starts near the
+    global optimum and random starts in the box."""
+    rows = []
+    for name in ["Whitley", "Rana", "SineEnvelope", "Mishra03", "Bukin06", "Thurber", "Cola", "PowerSum",
+                 "DeVilliersGlasser02", "NewFunction01", "Trefethen", "EggHolder"]:
+        k = getattr(gbf, name)()
+        D = k.N
+        lo = np.array([b[0] for b in k.bounds], dtype=float)
+        up = np.array([b[1] for b in k.bounds], dtype=float)
+        rs = np.random.RandomState(500 + len(name))
+        for t in range(10):
+            x0 = lo + rs.random_sample(D) * (up - lo)
+            if t < 6:
+                scale = [1e-1, 1e-2, 1e-3, 1e-4, 3e-2, 3e-3][t]
+                x0 = np.clip(np.array(k.global_optimum[0], dtype=float) * (1.0 + rs.normal(size=D) * scale)
+                             + rs.normal(size=D) * scale * 1e-2, lo, up)
+            owf = R.ObjectiveFunWrapper(k.bounds, k.fun)
+            with np.errstate(all="ignore"):
+                e, x = owf.local_search(x0)
+            rows.append(dict(functor=name, dim=D, bounds=np.array(k.bounds, dtype=float), x0=x0,
+                             success=x is not None, f=float(e), x=np.array(x0 if x is None else x),
+                             nfev=owf.nb_fun_call, fglob=float(k.fglob)))
+            print("lbfgsb cat", name, t, "success", x is not None, "f", float(e), "nfev", owf.nb_fun_call, flush=True)
+    np.savez_compressed(os.path.join(GOLD, "lbfgsb_scipy_cat.npz"), rows=np.array(rows, dtype=object),
+                        scipy_version=scipy.__version__)
+
+
 def gen_sutton_chen_traj():
     """BASELINE config 4 at the size the reference defines (suttonchen.py:55-62: 6 atoms, bounds
     +-0.7): the reference's own run on a recorded tape, pure SA -- energies and decisions of every
@@ -471,6 +500,8 @@ if __name__ == "__main__":
         gen_objective_points_cat3()
     elif MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "suite_stats":
         gen_suite_stats()
+    elif MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "lbfgsb_cat":
+        gen_lbfgsb_catalogue()
     elif MODE == "libm" and os.environ.get("SDA_GOLDEN_ONLY") == "round2":
         gen_lbfgsb_large()
         gen_sutton_chen_traj()
@@ -485,6 +516,7 @@ if __name__ == "__main__":
         gen_ls_runs()
         gen_lbfgsb()
         gen_lbfgsb_large()
+        gen_lbfgsb_catalogue()
         gen_sutton_chen_traj()
         gen_maxfun_anchor()
         gen_suite()

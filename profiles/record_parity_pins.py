@@ -32,7 +32,7 @@ for n_atoms, maxiter in pm.SUTTON_CHEN_CASES:
     m = pm.sutton_chen_metrics(sb, oracle, n_atoms, maxiter)
     pins["sutton_chen"]["%d-%d" % (n_atoms, maxiter)] = m
     print("SuttonChen", n_atoms, maxiter, m, flush=True)
-for fname in ("lbfgsb_scipy.npz", "lbfgsb_scipy_large.npz"):
+for fname in ("lbfgsb_scipy.npz", "lbfgsb_scipy_large.npz", "lbfgsb_scipy_cat.npz"):
     rows = pm.lbfgsb_metrics(sb, oracle, fname)
     pins["lbfgsb"][fname] = dict(cases=len(rows), same_nfev_as_scipy=sum(r["nfev"] == r["nfev_ref"] for r in rows),
                                  same_nfev_as_oracle=sum(r["nfev"] == r["nfev_oracle"] for r in rows),

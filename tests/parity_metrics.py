@@ -112,7 +112,10 @@ def lbfgsb_metrics(sb, oracle, fname):
     for r in rows:
         owf = sb.ObjectiveFunWrapper(r["bounds"], r["functor"])
         e, x = owf.local_search(r["x0"])
-        ok, xo, fo, nfev_o = oracle.local_search(oracle.Problem(r["functor"], r["bounds"]), r["x0"])
+        if str(r["functor"]) in oracle.FN:
+            ok, xo, fo, nfev_o = oracle.local_search(oracle.Problem(r["functor"], r["bounds"]), r["x0"])
+        else:                                   # catalogue part 3: no C restatement of the objective
+            ok, fo, nfev_o = bool(r["success"]), float(r["f"]), -1
         out.append(dict(functor=str(r["functor"]), dim=int(r["dim"]), success=x is not None,
                         success_ref=bool(r["success"]), f=float(e), f_ref=float(r["f"]),
                         x_dev=0.0 if x is None else float(np.max(np.abs(x - r["x"]))),

@@ -270,7 +270,10 @@ def test_trajectory_replay_against_reference(sb, oracle, fname):
     assert m["status"] == 0 and m["nit_ok"] and m["ncall_ok"]
     assert m["first_diff"] >= pin["first_diff"], (m["first_diff"], pin["first_diff"])
     assert m["first_diff"] >= min(m["n_evals"], 4000)
-    assert m["max_edev"] <= min(TRAJ_RTOL, max(4.0 * pin["max_edev"], 1e-13)), (m["max_edev"], pin["max_edev"])
+    # Sutton-Chen: the r^-9 pair terms turn the same ~1e-7 absolute x error into ~1e-3 relative in the
+    # energy of a compressed cluster (pins: 3.6e-3 at 6 atoms); every other fixture stays below 1e-4
+    ceiling = 5e-2 if "SuttonChen" in fname else TRAJ_RTOL
+    assert m["max_edev"] <= min(ceiling, max(4.0 * pin["max_edev"], 1e-13)), (m["max_edev"], pin["max_edev"])
     if m["first_diff"] == m["n_evals"]:
         assert m["tape_ok"] and m["x_dev"] <= 2e-5
         assert m["fun"] == pytest.approx(m["fun_ref"], rel=1e-3, abs=1e-9)
@@ -305,7 +308,7 @@ def test_sutton_chen_chains_match_oracle(sb, oracle, n_atoms, maxiter):
     assert m["counts_ok"] and m["status_ok"]
     assert m["exact_chains"] >= pin["exact_chains"] - 1e-12, (m["exact_chains"], pin["exact_chains"])
     assert m["exact_chains"] >= 0.75
-    assert m["max_edev"] <= min(TRAJ_RTOL, max(4.0 * pin["max_edev"], 1e-13)), (m["max_edev"], pin["max_edev"])
+    assert m["max_edev"] <= min(5e-2, max(4.0 * pin["max_edev"], 1e-13)), (m["max_edev"], pin["max_edev"])
 
 
 def test_maxfun_is_a_soft_limit(sb):
@@ -341,11 +344,31 @@ def test_local_search_against_scipy_and_oracle(sb, oracle, fname):
         if not r["success"]:
             continue
         if r["functor"] in ("Rastrigin", "Sphere", "Exponential", "Schwefel01", "Schwefel26", "Ackley01"):
-            assert r["f"] == pytest.approx(r["f_ref"], rel=1e-6, abs=1e-8), (r["functor"], r["dim"])
+            # (absolute floor grows with D: Schwefel26 is 418.98 D minus a sum of the same size)
+            assert r["f"] == pytest.approx(r["f_ref"], rel=1e-6, abs=1e-8 * max(1.0, r["dim"] / 10.0)), (r["functor"], r["dim"])
             assert r["x_dev"] <= 2e-5 * r["x_scale"], (r["functor"], r["dim"], r["x_dev"])
     same = sum(r["nfev"] == r["nfev_ref"] for r in rows)
     assert same >= pin["same_nfev_as_scipy"], (same, pin["same_nfev_as_scipy"])
     assert same >= 0.6 * len(rows)
+
+
+def test_local_search_on_catalogue_functions_against_scipy(sb, oracle):
+    """The same against SciPy on the catalogue classes whose suite statistics hinge on the last digits
+    of the local search (Whitley, Rana, Bukin06, Thurber, Cola, PowerSum, DeVilliersGlasser02 ...:
+    tests/golden/lbfgsb_scipy_cat.npz, 120 cases, starts near the optimum and random starts).  These
+    are ill-conditioned on purpose (Bukin06's sqrt kink, DeVilliersGlasser02's exp/sin fit), so a
+    one-ulp difference in f can send the line search another way: asserted are the pinned counts of
+    cases with SciPy's success flag and with SciPy's exact call count, and -- where the call count is
+    SciPy's -- the same minimum."""
+    rows = pm.lbfgsb_metrics(sb, oracle, "lbfgsb_scipy_cat.npz")
+    pin = _pin("lbfgsb", "lbfgsb_scipy_cat.npz")
+    ok = sum(r["success"] == r["success_ref"] for r in rows)
+    same = sum(r["nfev"] == r["nfev_ref"] for r in rows)
+    assert ok >= pin["success_match"] and ok >= 0.95 * len(rows), (ok, pin["success_match"])
+    assert same >= pin["same_nfev_as_scipy"] and same >= 0.7 * len(rows), (same, pin["same_nfev_as_scipy"])
+    for r in rows:
+        if r["success"] and r["success_ref"] and r["nfev"] == r["nfev_ref"]:
+            assert r["f"] == pytest.approx(r["f_ref"], rel=1e-5, abs=1e-8), (r["functor"], r["f"], r["f_ref"])
 
 
 def test_local_search_zero_plateau_trap(sb):
@@ -619,3 +642,4 @@ def test_block_synchronous_local_search_launch_is_bit_identical(sb):
     for k in ("x", "fun", "nit", "ncall", "ncall_ls", "n_ls", "status"):
         np.testing.assert_array_equal(out["0"][k], out["1"][k])
     assert (out["1"].n_ls > 0).all() and (out["1"].status == 0).all()
+
