@@ -290,6 +290,19 @@ def run_ours(args):
                          jobs_partial=int(((ok > 0) & (ok < 1)).sum()),
                          evaluations=float(sum(u.values()["ncall_max"].sum() for u in units)))
 
+    # ---- configs 3 and 4 at their largest shapes (BASELINE: 65,536 chains at D = 1000 with local
+    # search; Sutton-Chen N = 512, 8,192 chains), rank 0, one launch each, CUDA events
+    # (profiles/shapes_bench.py runs the whole table) ------------------------------------------------
+    shapes = None
+    if args.shapes and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "profiles"))
+        import shapes_bench
+        import ctypes as C
+        pk = C.c_double()
+        _lib.check(_lib.lib().sda_fp64_peak(C.byref(pk), None, local_rank))
+        shapes = [shapes_bench.run_shape(*sh, reps=1, peak=pk.value, warm=False) for sh in shapes_bench.quick_shapes()]
+    sync()
+
     # ---- config 1 (README.md:28-39): latency of ONE run through the public API ------------------
     config1 = None
     if rank == 0:
@@ -379,7 +392,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": batch.d2h_bytes() * world,
                         "ms_per_step": float(np.mean(e2e_ms))},
                 "gpu_launches": launches[0] * world,
-                "roofline": roofline, "cpu_baseline": cpu, "suite": suite, "config1_latency": config1,
+                "roofline": roofline, "cpu_baseline": cpu, "suite": suite, "shapes": shapes, "config1_latency": config1,
                 "python_reference": PYTHON_REFERENCE,
                 "breakdown": {"evals_per_step": evals / args.steps,
                               "chain_steps_per_s": (evals - ls_evals) / total_s,
@@ -405,6 +418,8 @@ def main():
     ap.add_argument("--no-suite", dest="suite", action="store_false",
                     help="skip the config-5 leg (whole suite, 250 jobs x 100 runs)")
     ap.add_argument("--suite-runs", type=int, default=100)
+    ap.add_argument("--no-shapes", dest="shapes", action="store_false",
+                    help="skip the config-3 (D = 1000) / config-4 (N = 512) leg")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that print banners on fd 1 (NCCL's version
     # line at communicator creation) are pointed at stderr until the result is printed

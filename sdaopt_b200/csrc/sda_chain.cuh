@@ -41,6 +41,11 @@ struct DeviceArgs {
     unsigned long long *work_counter;
     int ls_maxiter;                 // clamp(6*dim, 100, 1000)  _sda.py:291-296
     int group;                      // lanes per chain (power of two <= 32)
+    // Large D: the chain rows (x_cur, x_vis, sv: 3 D doubles per chain) do not fit shared memory at a
+    // useful occupancy (D = 1000: 24 KB per chain + a 32 KB box per CTA left 3-4 warps per SM), so they
+    // live in this per-warp-slot region of the workspace instead, read and written with lane-striped
+    // (coalesced) accesses that the L1/L2 serve; the box stays in shared memory, once per CTA.
+    double *rows;                   // [n_slots * (32/group) * 3 * dim] or NULL: rows in shared memory
     // phased execution (annealing launch / local-search launch alternate, sda_kernels.cu)
     int phased, round, steps_per_round;
     struct ChainRec *recs;          // [n_chains] suspended chain state

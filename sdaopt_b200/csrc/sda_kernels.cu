@@ -168,7 +168,10 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 #define SDA_GUIDED_WAVES 1
 #endif
 #ifndef SDA_PHASED_MIN_BLOCKS
-#define SDA_PHASED_MIN_BLOCKS 3
+// resident CTAs per SM of the two instantiations without local-search code.  4 -> 64 registers, 32
+// warps per SM: same-box A/B on the headline shape (profiles/r2_ab_occupancy_estrin.log) 3 -> 4:
+// pure SA 1,209 -> 1,300 M evals/s, with local search 1,279 -> 1,352; 5 and 6 spill and lose.
+#define SDA_PHASED_MIN_BLOCKS 4
 #endif
 // MODE: kPersistent = annealing with in-kernel local search; kPhasedAnneal = annealing half of the
 // phased execution; kPureSa = pure_sa runs (no local-search code either: the same 80-register,
@@ -200,13 +203,15 @@ __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOC
     }
     __syncthreads();
     const Box bx = { lo, up, rg, irg };
-    double *warp_rows = smem + 4 * dim + (size_t)warp * NG * 3 * dim;
+    const long long slot = (long long)blockIdx.x * warps_per_block + warp;
+    const bool rows_global = a.rows != nullptr;
+    double *warp_rows = rows_global ? a.rows + (size_t)slot * NG * 3 * dim
+                                    : smem + 4 * dim + (size_t)warp * NG * 3 * dim;
     double *x_cur = warp_rows + (size_t)g.gid * 3 * dim;
     double *x_vis = x_cur + dim;
     double *sv = x_vis + dim;
-    const long long slot = (long long)blockIdx.x * warps_per_block + warp;
     double *ls_slot = a.ls_work ? a.ls_work + slot * a.ls_stride : nullptr;
-    double *ls_smem = NO_LS ? nullptr : smem + 4 * dim + (size_t)warps_per_block * NG * 3 * dim +
+    double *ls_smem = NO_LS ? nullptr : smem + 4 * dim + (rows_global ? 0 : (size_t)warps_per_block * NG * 3 * dim) +
                                              (size_t)warp * ls_smem_doubles();
     // a.phased && round > 0: the chains come from the ready queue and resume from their parked state
     // (also used by the non-PHASED instantiation to finish what the bounded rounds left over)
@@ -436,9 +441,11 @@ __global__ void __launch_bounds__(SYNC ? SDA_LS_SYNC_WARPS * 32 : 128, SYNC ? 16
     double *lo = smem, *up = smem + dim;
     for (int k = threadIdx.x; k < dim; k += blockDim.x) { lo[k] = a.lower[k]; up[k] = a.upper[k]; }
     __syncthreads();
-    double *xe = smem + 2 * dim + (size_t)warp * (dim + ls_smem_doubles());
-    double *ls_smem = xe + dim;
     const long long slot = (long long)blockIdx.x * wpb + warp;
+    // evaluation buffer of the warp: shared memory, or (large D) a row of its slot of a.rows
+    double *xe = a.rows ? a.rows + (size_t)slot * (SDA_WARP / a.group) * 3 * dim
+                        : smem + 2 * dim + (size_t)warp * (dim + ls_smem_doubles());
+    double *ls_smem = a.rows ? smem + 2 * dim + (size_t)warp * ls_smem_doubles() : xe + dim;
     double *ls_slot = a.ls_work + slot * a.ls_stride;
     const long long n_ls = a.qctl[kLsCount];
     int *ready_next = a.ready_q + (size_t)((a.round + 1) & 1) * a.n_chains;
@@ -871,7 +878,10 @@ struct LaunchPlan {
     long long slots;
 };
 
-static int plan_launch(int dim, long long n_chains, int pure_sa, int group, int min_blocks, LaunchPlan *lp)
+// rows_global: in/out.  In: -1 = decide here, 0/1 = forced.  Decision: the rows leave shared memory when
+// a full block (8 warps) would not reach the target residency with them (D >~ 230 for one chain per warp).
+static int plan_launch(int dim, long long n_chains, int pure_sa, int group, int min_blocks, LaunchPlan *lp,
+                       int *rows_global = nullptr)
 {
     int dev = 0, sms = 0, smem_max = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -885,8 +895,16 @@ static int plan_launch(int dim, long long n_chains, int pure_sa, int group, int 
     const size_t ls_per_warp = pure_sa ? 0 : (size_t)sda::ls_smem_doubles() * sizeof(double);
     // aim for SDA_ANNEAL_MIN_BLOCKS resident blocks: shrink the block before giving up residency
     const size_t budget = (size_t)smem_max / min_blocks - 1024;
-    while (wpb > 1 && (size_t)(4 + 3 * ng * wpb) * dim * sizeof(double) + wpb * ls_per_warp > budget) wpb >>= 1;
-    size_t smem = (size_t)(4 + 3 * ng * wpb) * dim * sizeof(double) + wpb * ls_per_warp;
+    int rg = rows_global ? *rows_global : 0;
+    if (rg < 0) {
+        rg = (size_t)(4 + 3 * ng * wpb) * dim * sizeof(double) + wpb * ls_per_warp > budget ? 1 : 0;
+        const char *env = getenv("SDA_ROWS_GLOBAL");
+        if (env) rg = atoi(env) != 0;
+    }
+    if (rows_global) *rows_global = rg;
+    const int rows_per_warp = rg ? 0 : 3 * ng;
+    while (wpb > 1 && (size_t)(4 + rows_per_warp * wpb) * dim * sizeof(double) + wpb * ls_per_warp > budget) wpb >>= 1;
+    size_t smem = (size_t)(4 + rows_per_warp * wpb) * dim * sizeof(double) + wpb * ls_per_warp;
     lp->group = group;
     lp->sms = sms;
     if (smem > (size_t)smem_max) return SDA_E_UNSUPPORTED;
@@ -912,9 +930,12 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // workspace layout: [counter 256B][temp table][sigmax table][xmin C*D][ls slots]
 //                   [parked-chain buffers of the phased execution: recs, rec_x, ready_q, ls_q]
 struct WsLayout {
-    size_t temp, sig, xmin, ls, recs, recx, rq, lq, total;
+    size_t temp, sig, xmin, ls, recs, recx, rq, lq, rows, total;
     long long ls_stride;
 };
+
+struct RunModeLite { int group; };
+static RunModeLite run_group(const SdaProblem *p, const SdaConfig *c, long long n_chains);
 
 static WsLayout workspace_layout(const SdaProblem *p, const SdaConfig *c, long long n_chains, long long slots)
 {
@@ -933,6 +954,13 @@ static WsLayout workspace_layout(const SdaProblem *p, const SdaConfig *c, long l
         w.recx = off; off += align256((size_t)n_chains * p->dim * sizeof(double));
         w.rq = off; off += align256((size_t)2 * n_chains * sizeof(int));
         w.lq = off; off += align256((size_t)n_chains * sizeof(int));
+    }
+    // chain rows of the large-D mapping (plan_launch decides whether they are used): every slot
+    w.rows = off;
+    {
+        const RunModeLite g = run_group(p, c, n_chains);
+        if ((size_t)(4 + 3 * (32 / g.group) * 8) * p->dim * sizeof(double) > 40000)     // may be chosen
+            off += align256((size_t)slots * (size_t)(32 / g.group) * 3 * p->dim * sizeof(double));
     }
     w.total = off;
     return w;
@@ -954,6 +982,14 @@ static bool use_phased(const SdaConfig *c, long long n_chains)
     // chains (8 k: -11 %, 16 k: +16 %, 32 k: +43 %, 64 k: +35 %); Sutton-Chen N=38 with 8 k chains
     // is 5x slower phased.  148 SMs x 4 CTAs x 4 warps = 2368 searches run concurrently.
     return n_chains >= 8LL * device_sms() * SDA_LS_MIN_BLOCKS * 4;
+}
+
+static RunModeLite run_group(const SdaProblem *p, const SdaConfig *c, long long n_chains)
+{
+    RunModeLite r;
+    r.group = (p->functor == SDA_FN_USER && c->rng_mode != SDA_RNG_TAPE)
+                  ? pick_group_user(p->dim) : pick_group(p->dim, c->rng_mode, n_chains);
+    return r;
 }
 
 static thread_local long long g_last_launches = 0;
@@ -1034,17 +1070,28 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     cudaStream_t stream = (cudaStream_t)stream_;
     LaunchPlan lp;
     const bool phased = use_phased(c, n_chains);
-    const int group = (p->functor == SDA_FN_USER && c->rng_mode != SDA_RNG_TAPE)
-                          ? pick_group_user(p->dim) : pick_group(p->dim, c->rng_mode, n_chains);
+    const int group = run_group(p, c, n_chains).group;
+    int rows_global = -1;
+    // pure SA on the production RNG: the lean instantiation (64 registers, 4 CTAs per SM) when several
+    // chains share a warp or when the rows are in global memory anyway (large D: occupancy is what
+    // hides their latency); one chain per warp with its rows in shared memory (128 < D <~ 230) keeps
+    // the 128-register instantiation (Sutton-Chen N=128 measured +28 % in round 1)
+    bool lean_sa = c->pure_sa && c->rng_mode != SDA_RNG_TAPE;
     rc = plan_launch(p->dim, n_chains, c->pure_sa || phased, group,
-                     (phased || (c->pure_sa && c->rng_mode != SDA_RNG_TAPE && group < 32)) ? SDA_PHASED_MIN_BLOCKS
-                                                                                          : SDA_ANNEAL_MIN_BLOCKS, &lp);
+                     (phased || lean_sa) ? SDA_PHASED_MIN_BLOCKS : SDA_ANNEAL_MIN_BLOCKS, &lp, &rows_global);
     if (rc) return rc;
+    if (lean_sa && group == 32 && !rows_global) {
+        lean_sa = false;
+        rows_global = -1;
+        rc = plan_launch(p->dim, n_chains, 1, group, SDA_ANNEAL_MIN_BLOCKS, &lp, &rows_global);
+        if (rc) return rc;
+    }
     const WsLayout wl = workspace_layout(p, c, n_chains, max_slots());
     const size_t off_temp = wl.temp, off_sig = wl.sig, off_xmin = wl.xmin, off_ls = wl.ls;
     const size_t off_recs = wl.recs, off_recx = wl.recx, off_rq = wl.rq, off_lq = wl.lq;
     const long long ls_stride = wl.ls_stride;
     if (wl.total > workspace_bytes) return SDA_E_WORKSPACE;
+    if (rows_global && wl.total == wl.rows) return SDA_E_WORKSPACE;      // layout did not reserve the rows
     char *ws = (char *)workspace;
 
     // K1 tables (host) -> device
@@ -1087,6 +1134,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     if (lsmax > 1000) lsmax = 1000;
     a.ls_maxiter = lsmax;
     a.group = lp.group;
+    a.rows = rows_global ? (double *)(ws + wl.rows) : NULL;
 
     const int threads = lp.warps_per_block * 32;
     if (phased) {
@@ -1113,7 +1161,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         const char *ls_env = getenv("SDA_LS_SYNC");
         const bool ls_sync = ls_env ? atoi(ls_env) == 1 : true;    // block-synchronous launch: default
         const int ls_wpb = ls_sync ? SDA_LS_SYNC_WARPS : 4;
-        const size_t ls_smem = ((size_t)2 * p->dim + (size_t)ls_wpb * (p->dim + sda::ls_smem_doubles())) * sizeof(double);
+        const size_t ls_smem = ((size_t)2 * p->dim + (size_t)ls_wpb * ((rows_global ? 0 : p->dim) + sda::ls_smem_doubles())) * sizeof(double);
         int ls_blocks = ls_sync ? lp.sms * (16 / SDA_LS_SYNC_WARPS) : lp.sms * SDA_LS_MIN_BLOCKS;
         if ((long long)ls_blocks * ls_wpb > max_slots()) ls_blocks = max_slots() / ls_wpb;
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPhasedAnneal>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
@@ -1144,7 +1192,8 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         // whatever is still parked (chains that posted a request in almost every step) is finished
         // by the persistent kernel, resuming from the ready queue
         LaunchPlan lp2;
-        rc = plan_launch(p->dim, n_chains, 0, lp.group, SDA_ANNEAL_MIN_BLOCKS, &lp2);
+        int rg2 = rows_global;
+        rc = plan_launch(p->dim, n_chains, 0, lp.group, SDA_ANNEAL_MIN_BLOCKS, &lp2, &rg2);
         if (rc) return rc;
         a.round = (int)n_rounds;
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp2.smem));
@@ -1157,8 +1206,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         LaunchTimer tm(stream, 0);
         sda::sda_anneal_kernel<true, sda::kPersistent><<<lp.blocks, threads, lp.smem, stream>>>(a);
-    } else if (c->pure_sa && lp.group < 32) {
-        // (one chain per warp, D > 256: the 128-register instantiation is faster -- Sutton-Chen N=128: +28 %)
+    } else if (lean_sa) {
         CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPureSa>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         LaunchTimer tm(stream, 0);
         sda::sda_anneal_kernel<false, sda::kPureSa><<<lp.blocks, threads, lp.smem, stream>>>(a);

@@ -87,6 +87,9 @@ __device__ __forceinline__ double cos_2pi(double v)
     const bool flip = a > 0.25;
     if (flip) a = __dsub_rn(0.5, a);                                     // exact; cos(2 pi t) = -cos(2 pi (1/2 - t))
     const double z = __dmul_rn(a, a);
+    // (Horner on purpose: Estrin's scheme shortens the dependency chain from 11 to 5 FMAs but costs
+    // three more multiplies and four more live registers -- measured 5 % SLOWER on the headline shape,
+    // profiles/r2_ab_occupancy_estrin.log: the launch is bound by issue slots, not by latency)
     double p = kCos2PiC[11];
 #pragma unroll
     for (int i = 10; i >= 0; --i) p = fma(p, z, kCos2PiC[i]);
