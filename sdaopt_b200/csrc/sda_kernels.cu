@@ -177,7 +177,10 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 // phased execution; kPureSa = pure_sa runs (no local-search code either: the same 80-register,
 // 3-CTA shape as the phased half, +11 % over running pure SA through the persistent instantiation).
 enum KernelMode { kPersistent = 0, kPhasedAnneal = 1, kPureSa = 2 };
-template <bool TAPE, int MODE>
+// GROWS: the chain rows live in a.rows (global memory, large D) instead of shared memory -- a template
+// parameter, not a run-time select, so that the shared-memory instantiation keeps LDS/STS addressing
+// (a run-time pointer select made every row access a generic load: -8 % on the headline shape).
+template <bool TAPE, int MODE, bool GROWS>
 __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOCKS : SDA_ANNEAL_MIN_BLOCKS)
     sda_anneal_kernel(const DeviceArgs a)
 {
@@ -204,9 +207,10 @@ __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOC
     __syncthreads();
     const Box bx = { lo, up, rg, irg };
     const long long slot = (long long)blockIdx.x * warps_per_block + warp;
-    const bool rows_global = a.rows != nullptr;
-    double *warp_rows = rows_global ? a.rows + (size_t)slot * NG * 3 * dim
-                                    : smem + 4 * dim + (size_t)warp * NG * 3 * dim;
+    constexpr bool rows_global = GROWS;
+    double *warp_rows;
+    if constexpr (GROWS) warp_rows = a.rows + (size_t)slot * NG * 3 * dim;
+    else warp_rows = smem + 4 * dim + (size_t)warp * NG * 3 * dim;
     double *x_cur = warp_rows + (size_t)g.gid * 3 * dim;
     double *x_vis = x_cur + dim;
     double *sv = x_vis + dim;
@@ -427,8 +431,11 @@ __global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOC
 #ifndef SDA_LS_SYNC_WARPS
 #define SDA_LS_SYNC_WARPS 8     // two CTAs (two clocks) per SM; 16 and 4 measured 7 % and 4.5 % slower
 #endif
-template <bool SYNC>
-__global__ void __launch_bounds__(SYNC ? SDA_LS_SYNC_WARPS * 32 : 128, SYNC ? 16 / SDA_LS_SYNC_WARPS : SDA_LS_MIN_BLOCKS)
+#ifndef SDA_LS_SYNC_BLOCKS
+#define SDA_LS_SYNC_BLOCKS 2    // resident CTAs (clocks) per SM of the synchronous launch
+#endif
+template <bool SYNC, bool GROWS>
+__global__ void __launch_bounds__(SYNC ? SDA_LS_SYNC_WARPS * 32 : 128, SYNC ? SDA_LS_SYNC_BLOCKS : SDA_LS_MIN_BLOCKS)
     sda_ls_phase_kernel(const DeviceArgs a)
 {
     extern __shared__ double smem[];
@@ -443,9 +450,14 @@ __global__ void __launch_bounds__(SYNC ? SDA_LS_SYNC_WARPS * 32 : 128, SYNC ? 16
     __syncthreads();
     const long long slot = (long long)blockIdx.x * wpb + warp;
     // evaluation buffer of the warp: shared memory, or (large D) a row of its slot of a.rows
-    double *xe = a.rows ? a.rows + (size_t)slot * (SDA_WARP / a.group) * 3 * dim
-                        : smem + 2 * dim + (size_t)warp * (dim + ls_smem_doubles());
-    double *ls_smem = a.rows ? smem + 2 * dim + (size_t)warp * ls_smem_doubles() : xe + dim;
+    double *xe, *ls_smem;
+    if constexpr (GROWS) {
+        xe = a.rows + (size_t)slot * (SDA_WARP / a.group) * 3 * dim;
+        ls_smem = smem + 2 * dim + (size_t)warp * ls_smem_doubles();
+    } else {
+        xe = smem + 2 * dim + (size_t)warp * (dim + ls_smem_doubles());
+        ls_smem = xe + dim;
+    }
     double *ls_slot = a.ls_work + slot * a.ls_stride;
     const long long n_ls = a.qctl[kLsCount];
     int *ready_next = a.ready_q + (size_t)((a.round + 1) & 1) * a.n_chains;
@@ -992,6 +1004,8 @@ static RunModeLite run_group(const SdaProblem *p, const SdaConfig *c, long long 
     return r;
 }
 
+typedef void (*SdaKernelFn)(const DeviceArgs);
+
 static thread_local long long g_last_launches = 0;
 extern "C" long long sda_last_launch_count(void) { return g_last_launches; }
 
@@ -1071,7 +1085,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     LaunchPlan lp;
     const bool phased = use_phased(c, n_chains);
     const int group = run_group(p, c, n_chains).group;
-    int rows_global = -1;
+    int rows_global = c->rng_mode == SDA_RNG_TAPE ? 0 : -1;      // tape replay is serial: rows stay in shared memory
     // pure SA on the production RNG: the lean instantiation (64 registers, 4 CTAs per SM) when several
     // chains share a warp or when the rows are in global memory anyway (large D: occupancy is what
     // hides their latency); one chain per warp with its rows in shared memory (128 < D <~ 230) keeps
@@ -1162,23 +1176,25 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         const bool ls_sync = ls_env ? atoi(ls_env) == 1 : true;    // block-synchronous launch: default
         const int ls_wpb = ls_sync ? SDA_LS_SYNC_WARPS : 4;
         const size_t ls_smem = ((size_t)2 * p->dim + (size_t)ls_wpb * ((rows_global ? 0 : p->dim) + sda::ls_smem_doubles())) * sizeof(double);
-        int ls_blocks = ls_sync ? lp.sms * (16 / SDA_LS_SYNC_WARPS) : lp.sms * SDA_LS_MIN_BLOCKS;
+        int ls_blocks = ls_sync ? lp.sms * SDA_LS_SYNC_BLOCKS : lp.sms * SDA_LS_MIN_BLOCKS;
         if ((long long)ls_blocks * ls_wpb > max_slots()) ls_blocks = max_slots() / ls_wpb;
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPhasedAnneal>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        if (ls_sync) CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
-        else CK(cudaFuncSetAttribute(sda::sda_ls_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+        const SdaKernelFn k_anneal = rows_global ? sda::sda_anneal_kernel<false, sda::kPhasedAnneal, true>
+                                                 : sda::sda_anneal_kernel<false, sda::kPhasedAnneal, false>;
+        const SdaKernelFn k_ls = ls_sync ? (rows_global ? sda::sda_ls_phase_kernel<true, true> : sda::sda_ls_phase_kernel<true, false>)
+                                         : (rows_global ? sda::sda_ls_phase_kernel<false, true> : sda::sda_ls_phase_kernel<false, false>);
+        CK(cudaFuncSetAttribute(k_anneal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        CK(cudaFuncSetAttribute(k_ls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
         const bool debug_rounds = getenv("SDA_DEBUG_ROUNDS") != nullptr;
         for (long long r = 0; r < n_rounds; ++r) {
             a.round = (int)r;
             {
                 LaunchTimer tm(stream, 0);
-                sda::sda_anneal_kernel<false, sda::kPhasedAnneal><<<lp.blocks, threads, lp.smem, stream>>>(a);
+                k_anneal<<<lp.blocks, threads, lp.smem, stream>>>(a);
             }
             sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 0);
             {
                 LaunchTimer tm(stream, 1);
-                if (ls_sync) sda::sda_ls_phase_kernel<true><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
-                else sda::sda_ls_phase_kernel<false><<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
+                k_ls<<<ls_blocks, ls_wpb * 32, ls_smem, stream>>>(a);
             }
             sda::sda_rotate_kernel<<<1, 1, 0, stream>>>(a.qctl, 1);
             if (debug_rounds) {     // SDA_DEBUG_ROUNDS=1: queue lengths per round on stderr (synchronises!)
@@ -1196,24 +1212,24 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         rc = plan_launch(p->dim, n_chains, 0, lp.group, SDA_ANNEAL_MIN_BLOCKS, &lp2, &rg2);
         if (rc) return rc;
         a.round = (int)n_rounds;
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp2.smem));
+        const SdaKernelFn k_resume = rows_global ? sda::sda_anneal_kernel<false, sda::kPersistent, true>
+                                                 : sda::sda_anneal_kernel<false, sda::kPersistent, false>;
+        CK(cudaFuncSetAttribute(k_resume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp2.smem));
         {
             LaunchTimer tm(stream, 2);
-            sda::sda_anneal_kernel<false, sda::kPersistent><<<lp2.blocks, lp2.warps_per_block * 32, lp2.smem, stream>>>(a);
+            k_resume<<<lp2.blocks, lp2.warps_per_block * 32, lp2.smem, stream>>>(a);
         }
         g_last_launches = 4 * n_rounds + 1;
-    } else if (c->rng_mode == SDA_RNG_TAPE) {
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<true, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        LaunchTimer tm(stream, 0);
-        sda::sda_anneal_kernel<true, sda::kPersistent><<<lp.blocks, threads, lp.smem, stream>>>(a);
-    } else if (lean_sa) {
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPureSa>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        LaunchTimer tm(stream, 0);
-        sda::sda_anneal_kernel<false, sda::kPureSa><<<lp.blocks, threads, lp.smem, stream>>>(a);
     } else {
-        CK(cudaFuncSetAttribute(sda::sda_anneal_kernel<false, sda::kPersistent>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        SdaKernelFn k;
+        if (c->rng_mode == SDA_RNG_TAPE) k = sda::sda_anneal_kernel<true, sda::kPersistent, false>;    // (rows never global)
+        else if (lean_sa) k = rows_global ? sda::sda_anneal_kernel<false, sda::kPureSa, true>
+                                          : sda::sda_anneal_kernel<false, sda::kPureSa, false>;
+        else k = rows_global ? sda::sda_anneal_kernel<false, sda::kPersistent, true>
+                             : sda::sda_anneal_kernel<false, sda::kPersistent, false>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
         LaunchTimer tm(stream, 0);
-        sda::sda_anneal_kernel<false, sda::kPersistent><<<lp.blocks, threads, lp.smem, stream>>>(a);
+        k<<<lp.blocks, threads, lp.smem, stream>>>(a);
     }
     if (!phased) g_last_launches = 1;
     CK(cudaGetLastError());
