@@ -40,6 +40,7 @@ struct DeviceArgs {
     long long ls_stride;            // doubles per warp slot
     unsigned long long *work_counter;
     int ls_maxiter;                 // clamp(6*dim, 100, 1000)  _sda.py:291-296
+    int ls_memo;                    // finite-difference gradients of separable objectives from memoised terms
     int group;                      // lanes per chain (power of two <= 32)
     // Large D: the chain rows (x_cur, x_vis, sv: 3 D doubles per chain) do not fit shared memory at a
     // useful occupancy (D = 1000: 24 KB per chain + a 32 KB box per CTA left 3-4 warps per SM), so they

@@ -1006,6 +1006,13 @@ static RunModeLite run_group(const SdaProblem *p, const SdaConfig *c, long long 
 
 typedef void (*SdaKernelFn)(const DeviceArgs);
 
+// SDA_LS_MEMO=0: every perturbed point of a gradient evaluated in full (A/B switch; same bits either way)
+static int ls_memo_enabled(void)
+{
+    const char *env = getenv("SDA_LS_MEMO");
+    return env ? (atoi(env) != 0) : 1;
+}
+
 static thread_local long long g_last_launches = 0;
 extern "C" long long sda_last_launch_count(void) { return g_last_launches; }
 
@@ -1147,6 +1154,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
     if (lsmax < 100) lsmax = 100;
     if (lsmax > 1000) lsmax = 1000;
     a.ls_maxiter = lsmax;
+    a.ls_memo = ls_memo_enabled();
     a.group = lp.group;
     a.rows = rows_global ? (double *)(ws + wl.rows) : NULL;
 
@@ -1419,6 +1427,7 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
     if (lsmax < 100) lsmax = 100;
     if (lsmax > 1000) lsmax = 1000;
     a.ls_maxiter = lsmax;
+    a.ls_memo = ls_memo_enabled();
     CK(cudaFuncSetAttribute(sda::sda_local_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sda::sda_local_search_kernel<<<(int)blocks, wpb * 32, smem>>>(a, (const double *)dxi.p, n, (double *)dxo.p,
                                                                    (double *)dfo.p, (int *)dsu.p, (long long *)dnf.p);

@@ -33,7 +33,7 @@ constexpr double kGradEps = 1.e-6;   // self.reps                               
 __host__ __device__ inline long long ls_workspace_doubles(int n)
 {
     const int m = kLsM;
-    return 2LL * m * n + 9LL * n + 2LL * n + 8 + 4LL * m * m;
+    return 2LL * m * n + 9LL * n + 2LL * n + 2LL * n + 8 + 4LL * m * m;   // (+ 2 n: memoised terms ta, tb)
 }
 // shared-memory part: sy ss wt (m x m) | wn (2m x 2m) | wa (8m).  These are updated in place
 // element by element (Cholesky, triangular solves, running sums); through global memory every
@@ -47,6 +47,7 @@ struct LsWork {
     // SciPy's ScalarFunction keeps the last evaluated point: a request at a bit-identical x is
     // served from (xl, fl, gl) without calling the objective (no ncall, no monitor tick)
     double *xl, *gl;
+    double *ta, *tb;     // terms of the base point of a gradient (separable objectives, ls_fun_and_grad)
     double fl;
     int cache_valid;
     int *index, *iwhere, *indx2;
@@ -62,6 +63,7 @@ struct LsWork {
         ws = q; q += (long long)m * n;  wy = q; q += (long long)m * n;
         z = q; q += n;  r = q; q += n;  d = q; q += n;  t = q; q += n;  xp = q; q += n;
         g = q; q += n;  x = q; q += n;  xl = q; q += n;  gl = q; q += n;
+        ta = q; q += n;  tb = q; q += n;
         cache_valid = 0;
         index = reinterpret_cast<int *>(q);
         iwhere = index + n;
@@ -891,6 +893,18 @@ __device__ __noinline__ bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st
     // round r evaluates point e = 32 r + L by itself (even e: plus side of i = e/2, odd: minus).
     // Call counting and the suite monitor see them in the reference's order (:340-341).
     const long long mc0 = st.mon_calls;
+    // separable objective: the base point's terms once, lane-striped (sda_objectives.cuh)
+    const bool memo = a.ls_memo && objective_is_separable(a.functor);
+    const bool memo2 = memo && separable_has_second_sum(a.functor);
+    if (memo) {
+        for (int k = lane; k < n; k += SDA_WARP) {
+            double ta, tb;
+            separable_term(a.functor, xe[k], a.params, ta, tb);
+            w.ta[k] = ta;
+            if (memo2) w.tb[k] = tb;
+        }
+        __syncwarp();
+    }
     for (int e0 = 0; e0 < 2 * n; e0 += SDA_WARP) {
         const int e = e0 + lane;
         const bool valid = e < 2 * n;
@@ -903,7 +917,19 @@ __device__ __noinline__ bool ls_fun_and_grad(const DeviceArgs &a, ChainState &st
         double x2 = xi - respl;
         if (x2 < lo[i]) { x2 = lo[i]; respl = xi - x2; }
         double fe = 0.0;
-        if (valid) fe = eval_objective_solo_ool(a.functor, xe, i, plus ? x1 : x2, n, a.params, lane,
+        if (valid && memo) {
+            // f at the perturbed point: its own term i, every other term from the base point, summed in
+            // the order of the one-lane evaluation -> the same bits as eval_objective_solo_ool
+            double pa, pb, A = 0.0, B = 0.0;
+            separable_term(a.functor, plus ? x1 : x2, a.params, pa, pb);
+            #pragma unroll 4
+            for (int k = 0; k < n; ++k) A += (k == i) ? pa : w.ta[k];
+            if (memo2) {
+                #pragma unroll 4
+                for (int k = 0; k < n; ++k) B += (k == i) ? pb : w.tb[k];
+            }
+            fe = separable_finish(a.functor, A, B, n);
+        } else if (valid) fe = eval_objective_solo_ool(a.functor, xe, i, plus ? x1 : x2, n, a.params, lane,
                                                 (unsigned long long)(st.ncall + 1 + e));
         if (a.max_calls > 0) {
             const unsigned budget = __ballot_sync(SDA_FULL_MASK, valid && (mc0 + e + 1 >= a.max_calls));

@@ -295,6 +295,47 @@ struct PerturbedView {
     __device__ __forceinline__ double operator[](int k) const { return k == index ? value : x[k]; }
 };
 
+// ---- separable objectives: f = F(sum_k ta(x_k), sum_k tb(x_k)) -------------------------------------
+// Used by the finite-difference gradient of the local search (sda_lbfgsb.cuh): the 2 D perturbed points
+// of a gradient differ from the base point in ONE coordinate each, so all but one of the D terms of
+// every perturbed evaluation are the base point's terms.  They are computed once, and every perturbed
+// value is then summed from them IN THE SAME ORDER as the one-lane evaluation of eval_objective sums
+// (k = 0 .. D-1 from 0.0), so each of the 2 D values is bit-identical to the full evaluation -- the
+// expressions below are the same expressions as in eval_objective, and the library is built with
+// --fmad=false.  2 D + 1 evaluations of D transcendental terms become 3 D terms plus 2 D^2 additions.
+__device__ __forceinline__ bool objective_is_separable(int fid)
+{
+    return fid == SDA_FN_RASTRIGIN || fid == SDA_FN_SHIFTED_RASTRIGIN || fid == SDA_FN_ACKLEY01 ||
+           fid == SDA_FN_SCHWEFEL01 || fid == SDA_FN_SCHWEFEL26 || fid == SDA_FN_EXPONENTIAL ||
+           fid == SDA_FN_SPHERE;
+}
+__device__ __forceinline__ bool separable_has_second_sum(int fid) { return fid == SDA_FN_ACKLEY01; }
+
+__device__ __forceinline__ void separable_term(int fid, double v, const double *params, double &ta, double &tb)
+{
+    tb = 0.0;
+    switch (fid) {
+    case SDA_FN_RASTRIGIN: ta = v * v - 10.0 * cos_2pi(v); break;
+    case SDA_FN_SHIFTED_RASTRIGIN: { const double d = v - params[0]; ta = d * d - 10.0 * cos_2pi(d); break; }
+    case SDA_FN_ACKLEY01: ta = v * v; tb = cos_2pi(v); break;
+    case SDA_FN_SCHWEFEL26: ta = v * sin(sqrt(fabs(v))); break;
+    default: ta = v * v; break;                 // Schwefel01, Exponential, Sphere
+    }
+}
+
+__device__ __forceinline__ double separable_finish(int fid, double A, double B, int dim)
+{
+    switch (fid) {
+    case SDA_FN_RASTRIGIN: return 10.0 * dim + A;
+    case SDA_FN_SHIFTED_RASTRIGIN: return A + 10.0 * dim;
+    case SDA_FN_ACKLEY01: return -20. * exp(-0.2 * sqrt(A / dim)) - exp(B / dim) + 20. + 2.718281828459045;
+    case SDA_FN_SCHWEFEL01: return pow(A, 1.7724538509055159);
+    case SDA_FN_SCHWEFEL26: return 418.982887 * dim - A;
+    case SDA_FN_EXPONENTIAL: return -exp(-0.5 * A);
+    default: return A;                          // Sphere
+    }
+}
+
 // Out-of-line copy for the cold callers (local search, (re)initialisation): the body with all
 // registered objectives is ~4.5 K instructions, and inlining it at every call site grew the
 // L-BFGS-B code to 750 KB -- ncu showed 85 % of its cycles stalled on instruction fetch.
