@@ -671,3 +671,48 @@ def test_memoised_gradient_terms_are_bit_identical(sb):
             os.environ.pop("SDA_LS_MEMO", None)
         else:
             os.environ["SDA_LS_MEMO"] = keep
+
+
+def test_results_do_not_depend_on_batch_size_at_fixed_group_width(sb):
+    """A chain is a pure function of (problem, config, Philox key, lanes per chain).  The library picks
+    the lanes per chain from the dimension AND the batch size (small batches get wider groups), and the
+    partial sums of an objective follow the lane count -- so across batch sizes results are guaranteed
+    identical only at a fixed width (SDA_GROUP), which is what a sharded run that must reproduce a
+    single-GPU run bit for bit sets.  Pinned here: same keys, batches of 7 / 300 / 5,000 chains."""
+    keep = os.environ.get("SDA_GROUP")
+    try:
+        os.environ["SDA_GROUP"] = "8"
+        f = sb.Rastrigin(50)
+        seeds = np.arange(5000, dtype=np.uint64) + np.uint64(99)
+        big = sb.sda_batch(f, f.bounds, 5000, seeds=seeds, maxiter=12)
+        for n in (7, 300):
+            small = sb.sda_batch(f, f.bounds, n, seeds=seeds[:n], maxiter=12)
+            for k in ("x", "fun", "nit", "ncall", "ncall_ls", "n_ls"):
+                np.testing.assert_array_equal(small[k], big[k][:n], err_msg="%d %s" % (n, k))
+    finally:
+        if keep is None:
+            os.environ.pop("SDA_GROUP", None)
+        else:
+            os.environ["SDA_GROUP"] = keep
+
+
+def test_concurrent_host_threads_with_different_problems(sb):
+    """sda_batch_run from two host threads at once (ctypes releases the GIL), different dimensions and
+    batch sizes: the workspace layout is per call (no file-scope state), so each thread gets exactly
+    what it gets alone."""
+    import threading
+    jobs = [(sb.Rastrigin(50), 20000, dict(maxiter=10)), (sb.Schwefel26(7), 333, dict(maxiter=50)),
+            (sb.Ackley01(100), 900, dict(maxiter=6)), (sb.Rosenbrock(2), 64, dict(maxiter=200))]
+    alone = [sb.sda_batch(f, f.bounds, n, **kw) for f, n, kw in jobs]
+    for _ in range(3):
+        got = [None] * len(jobs)
+
+        def work(i):
+            f, n, kw = jobs[i]
+            got[i] = sb.sda_batch(f, f.bounds, n, **kw)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for a, b in zip(alone, got):
+            for k in ("x", "fun", "nit", "ncall", "ncall_ls", "n_ls", "status"):
+                np.testing.assert_array_equal(a[k], b[k])
