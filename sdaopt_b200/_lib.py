@@ -112,13 +112,14 @@ def lib(path=None):
         L.sda_kernel_timing.argtypes = [C.c_int]
         L.sda_math_probe_host.restype = C.c_int
         L.sda_math_probe_host.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
-        L.sda_functor_arity.restype = C.c_int
-        L.sda_functor_arity.argtypes = [C.c_int]
-        L.sda_energy_reset_host.restype = C.c_int
-        L.sda_energy_reset_host.argtypes = [C.POINTER(SdaProblem), C.c_void_p, C.c_void_p, C.c_int64,
-                                            C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
-                                            C.POINTER(C.c_double), C.POINTER(C.c_int32),
-                                            C.POINTER(C.c_int64), C.c_int]
+        if hasattr(L, "sda_functor_arity"):      # (absent from round-1 builds loaded through SDA_LIB_PATH for A/B runs)
+            L.sda_functor_arity.restype = C.c_int
+            L.sda_functor_arity.argtypes = [C.c_int]
+            L.sda_energy_reset_host.restype = C.c_int
+            L.sda_energy_reset_host.argtypes = [C.POINTER(SdaProblem), C.c_void_p, C.c_void_p, C.c_int64,
+                                                C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
+                                                C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                                C.POINTER(C.c_int64), C.c_int]
         L.sda_kernel_times.restype = C.c_int
         L.sda_kernel_times.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         if L.sda_abi_version() != 1:

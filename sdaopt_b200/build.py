@@ -33,8 +33,17 @@ def _include_flags():
 # of 260 s for the 198-functor library; a fixed count keeps the build reproducible across hosts).
 # Measured on B200 against the unsplit build: pure SA +9 %, block-synchronous local search +2 %.
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "--fmad=false", "-split-compile=8", "-Xcompiler", "-fPIC", "-shared",
-              "-diag-suppress", "177"]
+              "--fmad=false", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
+# ptxas compiles the dispatch over the registered objectives either as compare chains or as jump tables
+# (BRX through the kernel's constant bank 2), and which one it picks flips with the -split-compile
+# partitioning -- even between builds of identical sources from different directories.  With jump
+# tables the annealing launch is 6-8 % slower on the headline shape (same-box A/B of six builds,
+# profiles/r2_ab_split_compile_bisect.log: 1,330 vs 1,212-1,248 M evaluations/s, always paired with
+# CONSTANT[2] of the lean annealing kernel at 56-340 vs 1,172-1,488 bytes).  The build therefore checks
+# that figure with cuobjdump and walks through partition counts until it gets the compare chains.
+SPLIT_COUNTS = (4, 8, 6, 3, 5, 2)
+LEAN_KERNEL = "sda_anneal_kernelILb0ELi1ELb0"        # <philox, kPhasedAnneal, rows in shared memory>
+JUMP_TABLE_BYTES_MAX = 512
 
 
 def _nvcc():
@@ -52,20 +61,44 @@ def stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def constant_bank2_bytes(lib, kernel=LEAN_KERNEL):
+    """CONSTANT[2] (compiler-generated constants: jump tables) of `kernel` in `lib`, or None."""
+    cuobjdump = os.path.join(os.path.dirname(_nvcc()), "cuobjdump")
+    if not os.path.exists(cuobjdump):
+        return None
+    out = subprocess.run([cuobjdump, "-res-usage", lib], capture_output=True, text=True).stdout.splitlines()
+    for i, line in enumerate(out):
+        if kernel in line and i + 1 < len(out):
+            for tok in out[i + 1].split():
+                if tok.startswith("CONSTANT[2]:"):
+                    return int(tok.split(":")[1])
+            return 0            # no bank-2 entry: no compiler constants at all
+    return None
+
+
 def build(force=False, verbose=False):
     """Compile the CUDA library if it is missing or older than its sources."""
     if not force and not stale():
         return LIB
     extra = os.environ.get("SDA_NVCC_EXTRA", "").split()
-    cmd = [_nvcc()] + NVCC_FLAGS + _include_flags() + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    counts = SPLIT_COUNTS
+    if os.environ.get("SDA_SPLIT_COMPILE"):
+        counts = (int(os.environ["SDA_SPLIT_COMPILE"]),)
+    for n, split in enumerate(counts):
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-split-compile=%d" % split] + _include_flags() + extra + \
+              (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        subprocess.check_call(cmd)
+        c2 = constant_bank2_bytes(LIB)
+        print("sdaopt_b200.build: -split-compile=%d -> CONSTANT[2] of the lean annealing kernel: %s bytes"
+              % (split, c2), file=sys.stderr)
+        if c2 is None or c2 <= JUMP_TABLE_BYTES_MAX or n + 1 == len(counts):
+            break
     return LIB
 
 
 def build_user(header_path, out_path):
     """The same library with a user-supplied device functor compiled in as SDA_FN_USER."""
-    cmd = [_nvcc()] + NVCC_FLAGS + _include_flags() + ['-DSDA_USER_FUNCTOR_HEADER="%s"' % os.path.abspath(header_path),
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-split-compile=%d" % SPLIT_COUNTS[0]] + _include_flags() + ['-DSDA_USER_FUNCTOR_HEADER="%s"' % os.path.abspath(header_path),
                                     "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return out_path

@@ -182,7 +182,7 @@ __device__ __forceinline__ double fmod_exact(double a, double R, double invR)
     const double aa = fabs(a);
     if (aa < R) return a;
     const double q = aa * invR;
-    if (!(q < 1125899906842624.0)) return fmod(a, R);      // 2^50: fall back (also inf/nan)
+    if (!(q < 1125899906842624.0)) return cold_fmod(a, R);      // 2^50: fall back (also inf/nan)
     const double qi = __dadd_rn(__dadd_rn(q, 6755399441055744.0), -6755399441055744.0);
     double t = __fma_rn(-qi, R, aa);
     if (t < 0.0) t = __dadd_rn(t, R);
@@ -200,7 +200,7 @@ __device__ __forceinline__ double wrap_coord(double xv, double lower, double ran
     double m = b;
     if (m >= range) m = __dsub_rn(m, range);
     if (m >= range) m = __dsub_rn(m, range);
-    if (!(b <= 2.0 * range && b >= 0.0)) m = fmod(b, range);   // not reachable for finite inputs
+    if (!(b <= 2.0 * range && b >= 0.0)) m = cold_fmod(b, range);   // not reachable for finite inputs
     double r = __dadd_rn(m, lower);
     if (fabs(__dsub_rn(r, lower)) < kMinVisitBound) r = __dadd_rn(r, 1.e-10);
     return r;

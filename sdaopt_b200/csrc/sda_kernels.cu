@@ -169,9 +169,10 @@ __device__ __forceinline__ int call_energy_reset(const DeviceArgs &a, ChainState
 #endif
 #ifndef SDA_PHASED_MIN_BLOCKS
 // resident CTAs per SM of the two instantiations without local-search code.  4 -> 64 registers, 32
-// warps per SM: same-box A/B on the headline shape (profiles/r2_ab_occupancy_estrin.log) 3 -> 4:
-// pure SA 1,209 -> 1,300 M evals/s, with local search 1,279 -> 1,352; 5 and 6 spill and lose.
-#define SDA_PHASED_MIN_BLOCKS 4
+// warps per SM) wins the first, hot third of a run (same-box A/B on the headline shape at maxiter 100 / 300,
+// profiles/r2_ab_occupancy_estrin.log: +7 % / +6 %) but loses it back at low temperature: over the
+// whole maxiter = 1000 run 3 is 1.5 % faster (7.26 vs 7.37 s, profiles/r2_ab_split_compile_bisect.log).
+#define SDA_PHASED_MIN_BLOCKS 3
 #endif
 // MODE: kPersistent = annealing with in-kernel local search; kPhasedAnneal = annealing half of the
 // phased execution; kPureSa = pure_sa runs (no local-search code either: the same 80-register,
@@ -180,8 +181,12 @@ enum KernelMode { kPersistent = 0, kPhasedAnneal = 1, kPureSa = 2 };
 // GROWS: the chain rows live in a.rows (global memory, large D) instead of shared memory -- a template
 // parameter, not a run-time select, so that the shared-memory instantiation keeps LDS/STS addressing
 // (a run-time pointer select made every row access a generic load: -8 % on the headline shape).
+#ifndef SDA_GROWS_MIN_BLOCKS
+#define SDA_GROWS_MIN_BLOCKS 4   // rows in global memory: occupancy hides their latency (64 registers, 32 warps/SM)
+#endif
 template <bool TAPE, int MODE, bool GROWS>
-__global__ void __launch_bounds__(256, MODE != kPersistent ? SDA_PHASED_MIN_BLOCKS : SDA_ANNEAL_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, MODE != kPersistent ? (GROWS ? SDA_GROWS_MIN_BLOCKS : SDA_PHASED_MIN_BLOCKS)
+                                                           : SDA_ANNEAL_MIN_BLOCKS)
     sda_anneal_kernel(const DeviceArgs a)
 {
     constexpr bool PHASED = MODE == kPhasedAnneal;
@@ -914,6 +919,7 @@ static int plan_launch(int dim, long long n_chains, int pure_sa, int group, int 
         if (env) rg = atoi(env) != 0;
     }
     if (rows_global) *rows_global = rg;
+    if (rg && min_blocks == SDA_PHASED_MIN_BLOCKS) min_blocks = SDA_GROWS_MIN_BLOCKS;    // lean kernel, global rows
     const int rows_per_warp = rg ? 0 : 3 * ng;
     while (wpb > 1 && (size_t)(4 + rows_per_warp * wpb) * dim * sizeof(double) + wpb * ls_per_warp > budget) wpb >>= 1;
     size_t smem = (size_t)(4 + rows_per_warp * wpb) * dim * sizeof(double) + wpb * ls_per_warp;

@@ -44,6 +44,16 @@ __constant__ double kLogC[10] = {
 
 constexpr double kMagicRint = 6755399441055744.0;   // 1.5 * 2^52
 
+// The special-case paths of the functions below go to libdevice.  They are (almost) never taken, but
+// libdevice is bitcode: left to itself the compiler may inline cos / log / fmod -- ~1.1 KB of literals in
+// the kernel's constant bank, ~100 bytes more stack, a longer hot loop -- and whether it does depended on
+// which -split-compile partition the caller landed in: two builds of IDENTICAL sources from different
+// directories ran the annealing launch at 1,306 and 1,221 M evaluations/s
+// (profiles/r2_ab_split_compile_bisect.log).  Out of line, the fast path is the same in every build.
+__device__ __noinline__ double cold_cos(double x) { return cos(x); }
+__device__ __noinline__ double cold_log(double x) { return log(x); }
+__device__ __noinline__ double cold_fmod(double a, double b) { return fmod(a, b); }
+
 // a / b and sqrt(x) for NORMAL positive b, x (and a normal quotient): MUFU seed (2^-23), two Newton
 // steps, one residual correction -- 8 branch-free instructions instead of libdevice's ~14 plus the
 // BSSY/CALL scaffolding of its special-case path.  Faithfully rounded: never more than 1 ulp off
@@ -81,7 +91,7 @@ __device__ __forceinline__ double cos_2pi(double v)
 #ifdef SDA_LIBDEVICE_MATH   // A/B switch: the libdevice calls this file replaces
     return cos(6.283185307179586476925286766559 * v);
 #endif
-    if (!(fabs(v) < 2251799813685248.0)) return cos(6.283185307179586476925286766559 * v);  // 2^51, inf, nan
+    if (!(fabs(v) < 2251799813685248.0)) return cold_cos(6.283185307179586476925286766559 * v);  // 2^51, inf, nan
     const double q = __dadd_rn(__dadd_rn(v, kMagicRint), -kMagicRint);   // rint(v)
     double a = fabs(__dsub_rn(v, q));                                    // exact, in [0, 0.5]
     const bool flip = a > 0.25;
@@ -129,7 +139,7 @@ __device__ __forceinline__ double log_pos(double x)
 #endif
     int hx = __double2hiint(x);
     const int lx = __double2loint(x);
-    if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u) return log(x);   // 0, denormal, negative, inf, nan
+    if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u) return cold_log(x);   // 0, denormal, negative, inf, nan
     int k = (hx >> 20) - 1023;
     hx &= 0x000fffff;
     const int i = (hx + 0x95f64) & 0x100000;                  // mantissa above sqrt(2): halve it

@@ -64,76 +64,15 @@ __device__ __forceinline__ double eval_sutton_chen(const XV &x, int dim, const G
     return group_sum(part, g);
 }
 
-// Evaluate objective `fid` at x[0..dim).  Warp-uniform arguments; warp-uniform result.
-// x is anything indexable: a pointer into shared memory, or a PerturbedView of it.
+// catalogue part 2 (ids 11..59), out of line
 template <class XV>
-__device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
-                                                 const double *params, const Group &g,
-                                                 unsigned long long salt = 0)
+__device__ __noinline__ double eval_catalogue2(int fid, const XV &x, int dim, const double *params,
+                                              const Group &g, unsigned long long salt)
 {
     const int lane = g.gl, SDA_STRIDE = g.G;
     double a = 0.0, b = 0.0;
+    (void)params; (void)salt;
     switch (fid) {
-    case SDA_FN_RASTRIGIN: {  // go_funcs_R.py:91   10*N + sum(x^2 - 10 cos(2 pi x))
-        for (int k = lane; k < dim; k += SDA_STRIDE) {
-            const double v = x[k];
-            a += v * v - 10.0 * cos_2pi(v);
-        }
-        return 10.0 * dim + group_sum(a, g);
-    }
-    case SDA_FN_SHIFTED_RASTRIGIN: {  // README.md:65-66
-        const double shift = params[0];
-        for (int k = lane; k < dim; k += SDA_STRIDE) {
-            const double d = x[k] - shift;
-            a += d * d - 10.0 * cos_2pi(d);
-        }
-        return group_sum(a, g) + 10.0 * dim;
-    }
-    case SDA_FN_ROSENBROCK:  // scipy.optimize.rosen: sum(100 (x[i+1]-x[i]^2)^2 + (1-x[i])^2)
-        for (int k = lane; k + 1 < dim; k += SDA_STRIDE) {
-            const double v = x[k];
-            const double t = x[k + 1] - v * v;
-            const double u = 1.0 - v;
-            a += 100.0 * (t * t) + u * u;
-        }
-        return group_sum(a, g);
-    case SDA_FN_ACKLEY01:  // go_funcs_A.py:45-48
-        for (int k = lane; k < dim; k += SDA_STRIDE) {
-            const double v = x[k];
-            a += v * v;
-            b += cos_2pi(v);
-        }
-        a = group_sum(a, g);
-        b = group_sum(b, g);
-        return -20. * exp(-0.2 * sqrt(a / dim)) - exp(b / dim) + 20. + 2.718281828459045;
-    case SDA_FN_SCHWEFEL01:  // go_funcs_S.py:335-336   (sum x^2) ** sqrt(pi)
-        for (int k = lane; k < dim; k += SDA_STRIDE) a += x[k] * x[k];
-        return pow(group_sum(a, g), 1.7724538509055159);
-    case SDA_FN_SCHWEFEL26:  // go_funcs_S.py:616
-        for (int k = lane; k < dim; k += SDA_STRIDE) {
-            const double v = x[k];
-            a += v * sin(sqrt(fabs(v)));
-        }
-        return 418.982887 * dim - group_sum(a, g);
-    case SDA_FN_EXPONENTIAL:  // go_funcs_E.py:306
-        for (int k = lane; k < dim; k += SDA_STRIDE) a += x[k] * x[k];
-        return -exp(-0.5 * group_sum(a, g));
-    case SDA_FN_SUTTON_CHEN:
-        return eval_sutton_chen(x, dim, g);
-    case SDA_FN_CONSTANT:
-        return params[0];
-    case SDA_FN_SPHERE:  // go_funcs_S.py:1159
-        for (int k = lane; k < dim; k += SDA_STRIDE) a += x[k] * x[k];
-        return group_sum(a, g);
-    case SDA_FN_GRIEWANK:  // go_funcs_G.py:173-175
-        b = 1.0;
-        for (int k = lane; k < dim; k += SDA_STRIDE) {
-            const double v = x[k];
-            a += v * v / 4000.0;
-            b *= cos(v / sqrt((double)(k + 1)));
-        }
-        return group_sum(a, g) - group_prod(b, g) + 1.0;
-
     // ---- catalogue widening; formulas: go_benchmark_functions/go_funcs_<initial>.py
     // n-D forms: lane `lane` of the group takes terms lane, lane+G, ...
     case SDA_FN_ALPINE01:  // sum |x sin x + 0.1 x|
@@ -276,13 +215,93 @@ __device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
     case SDA_FN_ACKLEY03: { const double p = x[0], q = x[1]; return -200 * exp(-0.02 * sqrt(p * p + q * q)) + 5 * exp(cos(3 * p) + sin(3 * q)); }
     case SDA_FN_ZIRILLI: { const double p = x[0], q = x[1], p2 = p * p; return 0.25 * (p2 * p2) - 0.5 * p2 + 0.1 * p + 0.5 * (q * q); }
     case SDA_FN_ADJIMAN: { const double p = x[0], q = x[1]; return cos(p) * sin(q) - p / (q * q + 1); }
+    default:
+        return nan_value();
+    }
+}
+
+// Evaluate objective `fid` at x[0..dim).  Warp-uniform arguments; warp-uniform result.
+// x is anything indexable: a pointer into shared memory, or a PerturbedView of it.
+template <class XV>
+__device__ __forceinline__ double eval_objective(int fid, const XV &x, int dim,
+                                                 const double *params, const Group &g,
+                                                 unsigned long long salt = 0)
+{
+    const int lane = g.gl, SDA_STRIDE = g.G;
+    double a = 0.0, b = 0.0;
+    switch (fid) {
+    case SDA_FN_RASTRIGIN: {  // go_funcs_R.py:91   10*N + sum(x^2 - 10 cos(2 pi x))
+        for (int k = lane; k < dim; k += SDA_STRIDE) {
+            const double v = x[k];
+            a += v * v - 10.0 * cos_2pi(v);
+        }
+        return 10.0 * dim + group_sum(a, g);
+    }
+    case SDA_FN_SHIFTED_RASTRIGIN: {  // README.md:65-66
+        const double shift = params[0];
+        for (int k = lane; k < dim; k += SDA_STRIDE) {
+            const double d = x[k] - shift;
+            a += d * d - 10.0 * cos_2pi(d);
+        }
+        return group_sum(a, g) + 10.0 * dim;
+    }
+    case SDA_FN_ROSENBROCK:  // scipy.optimize.rosen: sum(100 (x[i+1]-x[i]^2)^2 + (1-x[i])^2)
+        for (int k = lane; k + 1 < dim; k += SDA_STRIDE) {
+            const double v = x[k];
+            const double t = x[k + 1] - v * v;
+            const double u = 1.0 - v;
+            a += 100.0 * (t * t) + u * u;
+        }
+        return group_sum(a, g);
+    case SDA_FN_ACKLEY01:  // go_funcs_A.py:45-48
+        for (int k = lane; k < dim; k += SDA_STRIDE) {
+            const double v = x[k];
+            a += v * v;
+            b += cos_2pi(v);
+        }
+        a = group_sum(a, g);
+        b = group_sum(b, g);
+        return -20. * exp(-0.2 * sqrt(a / dim)) - exp(b / dim) + 20. + 2.718281828459045;
+    case SDA_FN_SCHWEFEL01:  // go_funcs_S.py:335-336   (sum x^2) ** sqrt(pi)
+        for (int k = lane; k < dim; k += SDA_STRIDE) a += x[k] * x[k];
+        return pow(group_sum(a, g), 1.7724538509055159);
+    case SDA_FN_SCHWEFEL26:  // go_funcs_S.py:616
+        for (int k = lane; k < dim; k += SDA_STRIDE) {
+            const double v = x[k];
+            a += v * sin(sqrt(fabs(v)));
+        }
+        return 418.982887 * dim - group_sum(a, g);
+    case SDA_FN_EXPONENTIAL:  // go_funcs_E.py:306
+        for (int k = lane; k < dim; k += SDA_STRIDE) a += x[k] * x[k];
+        return -exp(-0.5 * group_sum(a, g));
+    case SDA_FN_SUTTON_CHEN:
+        return eval_sutton_chen(x, dim, g);
+    case SDA_FN_CONSTANT:
+        return params[0];
+    case SDA_FN_SPHERE:  // go_funcs_S.py:1159
+        for (int k = lane; k < dim; k += SDA_STRIDE) a += x[k] * x[k];
+        return group_sum(a, g);
+    case SDA_FN_GRIEWANK:  // go_funcs_G.py:173-175
+        b = 1.0;
+        for (int k = lane; k < dim; k += SDA_STRIDE) {
+            const double v = x[k];
+            a += v * v / 4000.0;
+            b *= cos(v / sqrt((double)(k + 1)));
+        }
+        return group_sum(a, g) - group_prod(b, g) + 1.0;
 #ifdef SDA_USER_FUNCTOR_HEADER
     // user-supplied device functor: every lane of the group evaluates it (group-uniform result)
     case SDA_FN_USER:
         return ::sda_user_objective(x, dim, params);
 #endif
-    default:  // ids 60..: the rest of the catalogue, out of line (cold code)
-        return eval_catalogue(fid, x, dim, g, salt);
+
+    default:
+        // ids 11..59 and 60..: the catalogue, out of line.  Only the eleven named objectives above are
+        // inlined into the annealing loop: with sixty inlined cases the kernel was ~650 KB of SASS, and
+        // how the compiler dispatched that switch (one 287-entry jump table or not) flipped between
+        // builds of identical sources with -split-compile -- a 7 % swing on the headline shape
+        // (profiles/r2_ab_split_compile_bisect.log).  A call per evaluation is noise for these.
+        return fid < SDA_FN_AMGM ? eval_catalogue2(fid, x, dim, params, g, salt) : eval_catalogue(fid, x, dim, g, salt);
     }
 }
 
