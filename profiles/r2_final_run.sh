@@ -1,7 +1,9 @@
 #!/bin/bash
-# round-2 evidence run on one B200: GPU tests, smoke, bench (both arms), suite, config 3/4 table
+# round-2 evidence run on one B200: parity pins, GPU tests, smoke, bench (both arms), suite, config 3/4 table
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/r2_final_gpu.txt
+python profiles/record_parity_pins.py > gpurun_out/r2_final_pins.log 2>&1
+cp gpurun_out/gpu_pins.json tests/golden/gpu_pins.json
 (time timeout 1500 python -m pytest tests -m gpu -q) > gpurun_out/r2_final_pytest_gpu.log 2>&1
 tail -n 4 gpurun_out/r2_final_pytest_gpu.log
 (time python -c "import __graft_entry__ as g; g.smoke()") > gpurun_out/r2_final_smoke.log 2>&1

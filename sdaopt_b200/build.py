@@ -41,7 +41,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 # profiles/r2_ab_split_compile_bisect.log: 1,330 vs 1,212-1,248 M evaluations/s, always paired with
 # CONSTANT[2] of the lean annealing kernel at 56-340 vs 1,172-1,488 bytes).  The build therefore checks
 # that figure with cuobjdump and walks through partition counts until it gets the compare chains.
-SPLIT_COUNTS = (4, 8, 6, 3, 5, 2)
+SPLIT_COUNTS = (2, 4, 8, 6, 3, 5)
 LEAN_KERNEL = "sda_anneal_kernelILb0ELi1ELb0"        # <philox, kPhasedAnneal, rows in shared memory>
 JUMP_TABLE_BYTES_MAX = 512
 

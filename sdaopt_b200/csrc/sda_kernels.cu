@@ -1012,6 +1012,27 @@ static RunModeLite run_group(const SdaProblem *p, const SdaConfig *c, long long 
 
 typedef void (*SdaKernelFn)(const DeviceArgs);
 
+// A kernel's dynamic shared-memory ceiling is process-wide state of the function.  It is always set to
+// the DEVICE's opt-in maximum, never to the size of the launch at hand: two host threads launching the
+// same kernel for different problems raced on it ("too many resources requested for launch" in the
+// thread whose larger request came first -- tests: test_concurrent_host_threads_with_different_problems).
+// The ceiling does not affect occupancy; the size passed at launch does.
+template <class F>
+static cudaError_t allow_dynamic_smem(F fn, size_t need)
+{
+    int dev = 0, smem_max = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, fn);
+    if (e != cudaSuccess) return e;
+    const int limit = smem_max - (int)fa.sharedSizeBytes;         // static + dynamic <= the opt-in maximum
+    if (need > (size_t)limit) return cudaErrorInvalidValue;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+}
+
 // SDA_LS_MEMO=0: every perturbed point of a gradient evaluated in full (A/B switch; same bits either way)
 static int ls_memo_enabled(void)
 {
@@ -1196,8 +1217,8 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
                                                  : sda::sda_anneal_kernel<false, sda::kPhasedAnneal, false>;
         const SdaKernelFn k_ls = ls_sync ? (rows_global ? sda::sda_ls_phase_kernel<true, true> : sda::sda_ls_phase_kernel<true, false>)
                                          : (rows_global ? sda::sda_ls_phase_kernel<false, true> : sda::sda_ls_phase_kernel<false, false>);
-        CK(cudaFuncSetAttribute(k_anneal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
-        CK(cudaFuncSetAttribute(k_ls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+        CK(allow_dynamic_smem(k_anneal, lp.smem));
+        CK(allow_dynamic_smem(k_ls, ls_smem));
         const bool debug_rounds = getenv("SDA_DEBUG_ROUNDS") != nullptr;
         for (long long r = 0; r < n_rounds; ++r) {
             a.round = (int)r;
@@ -1228,7 +1249,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
         a.round = (int)n_rounds;
         const SdaKernelFn k_resume = rows_global ? sda::sda_anneal_kernel<false, sda::kPersistent, true>
                                                  : sda::sda_anneal_kernel<false, sda::kPersistent, false>;
-        CK(cudaFuncSetAttribute(k_resume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp2.smem));
+        CK(allow_dynamic_smem(k_resume, lp2.smem));
         {
             LaunchTimer tm(stream, 2);
             k_resume<<<lp2.blocks, lp2.warps_per_block * 32, lp2.smem, stream>>>(a);
@@ -1241,7 +1262,7 @@ extern "C" int sda_batch_run(const SdaProblem *p, const SdaConfig *c, int64_t n_
                                           : sda::sda_anneal_kernel<false, sda::kPureSa, false>;
         else k = rows_global ? sda::sda_anneal_kernel<false, sda::kPersistent, true>
                              : sda::sda_anneal_kernel<false, sda::kPersistent, false>;
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
+        CK(allow_dynamic_smem(k, lp.smem));
         LaunchTimer tm(stream, 0);
         k<<<lp.blocks, threads, lp.smem, stream>>>(a);
     }
@@ -1434,7 +1455,7 @@ extern "C" int sda_local_search_host(const SdaProblem *p, const double *x_in, in
     if (lsmax > 1000) lsmax = 1000;
     a.ls_maxiter = lsmax;
     a.ls_memo = ls_memo_enabled();
-    CK(cudaFuncSetAttribute(sda::sda_local_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(allow_dynamic_smem(sda::sda_local_search_kernel, smem));
     sda::sda_local_search_kernel<<<(int)blocks, wpb * 32, smem>>>(a, (const double *)dxi.p, n, (double *)dxo.p,
                                                                    (double *)dfo.p, (int *)dsu.p, (long long *)dnf.p);
     CK(cudaGetLastError());
@@ -1475,7 +1496,7 @@ extern "C" int sda_energy_reset_host(const SdaProblem *p, const double *x0, cons
     a.tape = (const double *)dt.p; a.tape_len = tape_len;
     a.fglob_tol = nan("");
     const size_t smem = 5 * D * sizeof(double);
-    CK(cudaFuncSetAttribute(sda::sda_energy_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(allow_dynamic_smem(sda::sda_energy_reset_kernel, smem));
     sda::sda_energy_reset_kernel<<<1, 32, smem>>>(a, (const double *)dx0.p, have_best ? 1 : 0, (double *)dxc.p,
                                                   (double *)dxb.p, (double *)dsc.p, (int *)dst.p, (long long *)dtu.p);
     CK(cudaGetLastError());
