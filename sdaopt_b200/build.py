@@ -39,9 +39,12 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 # partitioning -- even between builds of identical sources from different directories.  With jump
 # tables the annealing launch is 6-8 % slower on the headline shape (same-box A/B of six builds,
 # profiles/r2_ab_split_compile_bisect.log: 1,330 vs 1,212-1,248 M evaluations/s, always paired with
-# CONSTANT[2] of the lean annealing kernel at 56-340 vs 1,172-1,488 bytes).  The build therefore checks
-# that figure with cuobjdump and walks through partition counts until it gets the compare chains.
-SPLIT_COUNTS = (2, 4, 8, 6, 3, 5)
+# CONSTANT[2] of the lean annealing kernel at 56-340 vs 1,172-1,488 bytes).  It is not even a function of
+# the inputs: the same sources, path and flags gave both outcomes on different days (the partitions are
+# compiled by concurrent threads).  The build therefore checks that figure with cuobjdump, walks through
+# partition counts until it gets the compare chains, and never replaces an up-to-date library that has
+# them by one that does not.
+SPLIT_COUNTS = (4, 8, 6, 3)
 LEAN_KERNEL = "sda_anneal_kernelILb0ELi1ELb0"        # <philox, kPhasedAnneal, rows in shared memory>
 JUMP_TABLE_BYTES_MAX = 512
 
@@ -76,23 +79,39 @@ def constant_bank2_bytes(lib, kernel=LEAN_KERNEL):
     return None
 
 
+def _good(c2):
+    return c2 is None or c2 <= JUMP_TABLE_BYTES_MAX
+
+
 def build(force=False, verbose=False):
-    """Compile the CUDA library if it is missing or older than its sources."""
+    """Compile the CUDA library if it is missing or older than its sources (always with force=True).
+    Every attempt compiles to a side file; it replaces the in-tree library unless that one is up to date
+    and has the good dispatch codegen while the new one has not (see SPLIT_COUNTS)."""
     if not force and not stale():
         return LIB
     extra = os.environ.get("SDA_NVCC_EXTRA", "").split()
     counts = SPLIT_COUNTS
     if os.environ.get("SDA_SPLIT_COMPILE"):
         counts = (int(os.environ["SDA_SPLIT_COMPILE"]),)
+    keep_existing = (not stale()) and not extra and _good(constant_bank2_bytes(LIB))
+    tmp = LIB + ".new"
     for n, split in enumerate(counts):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-split-compile=%d" % split] + _include_flags() + extra + \
-              (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+              (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
         subprocess.check_call(cmd)
-        c2 = constant_bank2_bytes(LIB)
+        c2 = constant_bank2_bytes(tmp)
         print("sdaopt_b200.build: -split-compile=%d -> CONSTANT[2] of the lean annealing kernel: %s bytes"
               % (split, c2), file=sys.stderr)
-        if c2 is None or c2 <= JUMP_TABLE_BYTES_MAX or n + 1 == len(counts):
+        if _good(c2):
+            os.replace(tmp, LIB)
             break
+        if keep_existing:
+            print("sdaopt_b200.build: compiled; keeping the up-to-date library, whose dispatch codegen is the "
+                  "faster one", file=sys.stderr)
+            os.remove(tmp)
+            break
+        if n + 1 == len(counts):
+            os.replace(tmp, LIB)
     return LIB
 
 

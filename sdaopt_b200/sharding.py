@@ -26,8 +26,10 @@ def shard_by_cost(costs, world, rank):
 
 
 def chain_keys(base_seed, begin, end):
-    """Philox keys of the chains [begin, end): key = base_seed + global chain index, so results do
-    not depend on the number of ranks."""
+    """Philox keys of the chains [begin, end): key = base_seed + global chain index, so a chain's draws
+    do not depend on the number of ranks (nor do its results, as long as every rank's batch gets the
+    same lanes per chain: the library derives them from the dimension and the batch size, SDA_GROUP
+    pins them)."""
     return (np.arange(begin, end, dtype=np.uint64) + np.uint64(base_seed))
 
 
