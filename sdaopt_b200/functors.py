@@ -519,7 +519,15 @@ def compile_user_functor(source, params=(), name="user", bounds=None, fglob=floa
     the functor inlined (nvcc, about a minute, cached by source hash under build/user/) and the
     returned DeviceFunctor routes every call to that library.  No CPU evaluation ever happens."""
     from . import build as _build
-    digest = hashlib.sha1(source.encode()).hexdigest()[:16]
+    # cache key: the functor AND the kernels it is compiled into (a cached build of older kernels
+    # must not be picked up after the package's sources changed)
+    h = hashlib.sha1(source.encode())
+    for dep in sorted(_build.SOURCES + _build.HEADERS):
+        path = os.path.join(_build.CSRC, dep)
+        if os.path.exists(path):
+            with open(path, "rb") as fh:
+                h.update(fh.read())
+    digest = h.hexdigest()[:16]
     root = build_dir or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                      "build", "user", digest)
     os.makedirs(root, exist_ok=True)
