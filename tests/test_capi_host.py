@@ -215,3 +215,15 @@ def test_workspace_size_is_monotone():
     c = L.sda_workspace_bytes(C.byref(p), C.byref(cfg), 65536)
     assert 0 < a < b and c < b
     assert L.sda_workspace_bytes(None, C.byref(cfg), 4) == 0
+
+
+def test_build_reads_the_dispatch_codegen_of_the_library():
+    """sdaopt_b200/build.py decides between builds by the size of the annealing kernel's compiler
+    constant bank (jump tables: 6-8 % slower).  The parser must find the kernel in the built library."""
+    import shutil
+    from sdaopt_b200 import build
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump not available")
+    c2 = build.constant_bank2_bytes(build.LIB)
+    assert c2 is not None and 0 <= c2 < 1 << 20
+    assert build.constant_bank2_bytes(build.LIB, kernel="no_such_kernel") is None
